@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — CloudAAE hot-path benchmark (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One rank per GPU (torchrun for N > 1).  W untimed warm-up steps, then EXACTLY K timed steps
+bracketed by barrier + synchronize; rank 0 prints ONE JSON line.  Device time comes from CUDA
+events on the launching stream; the L2 is flushed between timed iterations (outside the event
+pairs).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+# ----------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops", 0)),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", 0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# Workload "ops": BASELINE.json configs[1] — the tf_ops microbench, batch 32:
+#   FPS 2048 -> 256 (+ fused gather) on 32 YCB-shaped clouds, then chamfer nn_distance forward and
+#   backward on 1024 x 1024 points (decoder-shaped prediction vs the first 1024 points of the cloud).
+# A "segment" is one cloud taken through that pass.
+OPS_B, OPS_N, OPS_M, OPS_CH = 32, 2048, 256, 1024
+
+
+def ycb_shaped_clouds(b: int, seed: int) -> np.ndarray:
+    """b posed YCB models, f32[b,2048,3]: committed fixture models x fixture poses (synthetic
+    selection by seed).  No occluder / visibility here — that belongs to the train workload."""
+    models = np.load(os.path.join(ROOT, "tests", "golden", "ycb_models_xyz.npy"))
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ycb_poses.npz"))
+    rng = np.random.default_rng(seed)
+    sel = rng.integers(0, len(z["class_id"]), b)
+    cls = z["class_id"][sel]
+    ax = z["axisangle"][sel].astype(np.float64)
+    theta = np.linalg.norm(ax, axis=1, keepdims=True)
+    k = ax / np.maximum(theta, 1e-12)
+    K = np.zeros((b, 3, 3))
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -k[:, 2], k[:, 1], k[:, 2]
+    K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -k[:, 0], -k[:, 1], k[:, 0]
+    R = np.eye(3)[None] + np.sin(theta)[:, :, None] * K + (1 - np.cos(theta))[:, :, None] * (K @ K)
+    pts = models[cls] @ np.transpose(R, (0, 2, 1)).astype(np.float32) + z["translation"][sel][:, None, :]
+    return np.ascontiguousarray(pts, dtype=np.float32)
+
+
+def ops_inputs(b: int, seed: int):
+    clouds = ycb_shaped_clouds(b, seed)
+    rng = np.random.default_rng(seed + 1000)
+    target = clouds[:, :OPS_CH, :]
+    pred = (target[:, rng.permutation(OPS_CH), :] + rng.standard_normal((b, OPS_CH, 3)).astype(np.float32) * 0.01)
+    return clouds, np.ascontiguousarray(pred, np.float32), np.ascontiguousarray(target, np.float32)
+
+
+def run_ours_ops(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import cloudaae_b200 as caae
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    peaks = measured_peaks()
+    B = OPS_B
+    clouds_h, pred_h, target_h = ops_inputs(B, seed=rank)
+    clouds = torch.from_numpy(clouds_h).to(dev)
+    pred = torch.from_numpy(pred_h).to(dev)
+    target = torch.from_numpy(target_h).to(dev)
+    gscale = torch.full((B, OPS_CH), 1.0 / (B * OPS_CH), device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step():
+        idx, sub = caae.farthest_point_sample_gather(OPS_M, clouds)
+        d1, i1, d2, i2 = caae.nn_distance(pred, target)
+        g1, g2 = caae.nn_distance_grad(pred, target, gscale, i1, gscale, i2)
+        return idx, sub, d1, d2, g1
+
+    # --- per-kernel timing for the roofline block (CUDA events on the launching stream)
+    def time_kernel(fn, iters):
+        evs = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream); fn(); e.record(stream)
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return float(np.mean([s.elapsed_time(e) for s, e in evs]))  # ms
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    events = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        step()
+        e.record(stream)
+        events.append((s, e))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    total_ms = float(sum(s.elapsed_time(e) for s, e in events))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # --- per-kernel breakdown + roofline of the dominant kernel
+    k_iters = max(5, min(args.steps, 50))
+    t_fps = time_kernel(lambda: caae.farthest_point_sample_gather(OPS_M, clouds), k_iters)
+    _, i1, _, i2 = caae.nn_distance(pred, target)
+    t_nnd = time_kernel(lambda: caae.nn_distance(pred, target), k_iters)
+    t_bwd = time_kernel(lambda: caae.nn_distance_grad(pred, target, gscale, i1, gscale, i2), k_iters)
+    fps_bytes = (12 * OPS_N + 4 * OPS_M) * B                 # 12n + 4m per cloud
+    nnd_bytes = 20 * (OPS_CH + OPS_CH) * B                   # 20(n+m) per cloud pair
+    bwd_bytes = 32 * (OPS_CH + OPS_CH) * B                   # 32(n+m) per cloud pair
+    kernels = {
+        "fps_2048_256": {"ms": t_fps, "algorithmic_bytes": fps_bytes, "gbs": fps_bytes / t_fps / 1e6,
+                         "rounds_per_s_per_cloud": (OPS_M - 1) / (t_fps * 1e-3),
+                         "gflops": 8.0 * OPS_N * (OPS_M - 1) * B / t_fps / 1e6},
+        "nn_distance_fwd_1024": {"ms": t_nnd, "algorithmic_bytes": nnd_bytes, "gbs": nnd_bytes / t_nnd / 1e6,
+                                 "gpairs_per_s": 2.0 * OPS_CH * OPS_CH * B / t_nnd / 1e6,
+                                 "gflops": 16.0 * OPS_CH * OPS_CH * B / t_nnd / 1e6},
+        "nn_distance_bwd_1024": {"ms": t_bwd, "algorithmic_bytes": bwd_bytes, "gbs": bwd_bytes / t_bwd / 1e6},
+    }
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": kernels[dom]["gbs"] / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peaks["source"],
+                "note": "FPS is a 255-round dependent chain (latency bound); GB/s on compulsory bytes as the metric asks"}
+
+    # --- e2e: the same pass through the public API with HOST buffers (pinned), copies inside the timed region
+    ph_c = torch.from_numpy(clouds_h).pin_memory(); ph_p = torch.from_numpy(pred_h).pin_memory()
+    ph_t = torch.from_numpy(target_h).pin_memory()
+    out_idx = torch.empty((B, OPS_M), dtype=torch.int32).pin_memory()
+    out_loss = torch.empty((B, OPS_CH), dtype=torch.float32).pin_memory()
+    out_g = torch.empty((B, OPS_CH, 3), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        c = ph_c.to(dev, non_blocking=True); p = ph_p.to(dev, non_blocking=True); t = ph_t.to(dev, non_blocking=True)
+        idx, sub = caae.farthest_point_sample_gather(OPS_M, c)
+        d1, i1, d2, i2 = caae.nn_distance(p, t)
+        g1, _ = caae.nn_distance_grad(p, t, gscale, i1, gscale, i2)
+        out_idx.copy_(idx, non_blocking=True); out_loss.copy_(d1 + d2, non_blocking=True)
+        out_g.copy_(g1, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = ph_c.numel() * 4 + ph_p.numel() * 4 + ph_t.numel() * 4
+    d2h = out_idx.numel() * 4 + out_loss.numel() * 4 + out_g.numel() * 4
+
+    if rank != 0:
+        return None
+    ms_per_step = total_ms / args.steps
+    result = {
+        "metric": "segments/sec (tf_ops microbench pass: FPS 2048->256 + gather + nn_distance fwd+bwd 1024x1024)",
+        "value": B * world / (ms_per_step * 1e-3), "unit": "segments/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (committed YCB model fixture x fixture poses)",
+        "config": {"workload": "tf_ops microbench, BASELINE.json configs[1]", "batch_per_gpu": B, "fps": [OPS_N, OPS_M],
+                   "nn_distance": [OPS_CH, OPS_CH], "l2": "flushed between timed iterations (256 MB write)",
+                   "parallelism": f"independent clouds sharded over {world} rank(s), no collective"},
+        "roofline": roofline, "kernels": kernels,
+        "e2e": {"value": B * world / (e2e_s / args.steps), "unit": "segments/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": 3 * args.steps, "clocks": clocks, "wall_s_timed_region": t_wall,
+    }
+    result["cpu_baseline"] = cpu_baseline_ops(sample_clouds=8)
+    return result
+
+
+# ----------------------------------------------------------------------------------------------
+def _ref_ops_pass(clouds, pred, target, threads):
+    """The reference's CPU implementation of the same pass, batch split over `threads` host threads.
+    nn_distance fwd+bwd: the reference's own NnDistance/NnDistanceGrad CPU OpKernels (oracle/_ref);
+    FPS + gather: oracle port of the CUDA kernel (the reference has no CPU FPS kernel)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import ops as O
+    b = clouds.shape[0]
+    use_ref = O.have_ref()
+    g = np.full((1, OPS_CH), 1.0 / (b * OPS_CH), np.float32)
+
+    def one(i):
+        idx = O.fps(clouds[i:i + 1], OPS_M, threads=1)
+        O.gather(clouds[i:i + 1], idx)
+        if use_ref:
+            d1, i1, d2, i2 = O.ref_cpu_nn_distance(pred[i:i + 1], target[i:i + 1])
+            O.ref_cpu_nn_distance_grad(pred[i:i + 1], target[i:i + 1], g, i1, g, i2)
+        else:
+            d1, i1, d2, i2 = O.nn_distance(pred[i:i + 1], target[i:i + 1], "cpu")
+            O.nn_distance_grad(pred[i:i + 1], target[i:i + 1], g, i1, g, i2)
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(b)))
+    return "reference" if use_ref else "port"
+
+
+def cpu_baseline_ops(sample_clouds: int):
+    threads = os.cpu_count() or 1
+    b = max(sample_clouds, threads)
+    clouds, pred, target = ops_inputs(b, seed=12345)
+    _ref_ops_pass(clouds[:threads], pred[:threads], target[:threads], threads)  # warm
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        kind = _ref_ops_pass(clouds, pred, target, threads)
+        reps += 1
+        if time.perf_counter() - t0 > 10.0 or reps >= 20:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": b * reps / dt, "unit": "segments/s", "cores": threads, "kind": kind,
+            "sample": f"{reps} x {b} clouds of the same pass (FPS via oracle port; nn_distance fwd+bwd via "
+                      f"{'the reference CPU OpKernels' if kind == 'reference' else 'the oracle port'}), "
+                      f"batch split over {threads} threads"}
+
+
+def run_reference_ops(args):
+    """--impl reference: the reference's CPU path on this box's host cores, same config/metric."""
+    threads = os.cpu_count() or 1
+    b = OPS_B
+    clouds, pred, target = ops_inputs(b, seed=0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        _ref_ops_pass(clouds, pred, target, threads)
+    t0 = time.perf_counter()
+    kind = "port"
+    for _ in range(args.steps):
+        kind = _ref_ops_pass(clouds, pred, target, threads)
+    dt = time.perf_counter() - t0
+    value = b * args.steps / dt
+    sample = f"{args.steps} steps x {b} clouds, full pass per step, batch split over {threads} host threads"
+    return {
+        "impl": "reference",
+        "metric": "segments/sec (tf_ops microbench pass: FPS 2048->256 + gather + nn_distance fwd+bwd 1024x1024)",
+        "value": value, "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (committed YCB model fixture x fixture poses)",
+        "config": {"workload": "tf_ops microbench, BASELINE.json configs[1]", "batch_per_gpu": b,
+                   "fps": [OPS_N, OPS_M], "nn_distance": [OPS_CH, OPS_CH]},
+        "cpu_baseline": {"value": value, "unit": "segments/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference_ops(args)), flush=True)
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        result = run_ours_ops(args, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps(result), flush=True)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

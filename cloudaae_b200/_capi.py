@@ -1,0 +1,93 @@
+"""ctypes binding of libcloudaae_b200.so (the C ABI declared in include/cloudaae_b200.h).
+
+There is no CPU fallback: if the library is missing or an entry point reports an error the call
+raises.  Tensors cross the boundary as raw device pointers plus the current CUDA stream handle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcloudaae_b200.so")
+
+ABI_VERSION = 1
+
+_int = ctypes.c_int
+_ptr = ctypes.c_void_p
+
+
+class InvalidArgumentError(ValueError):
+    """Shape/dtype violation — the role of tf.errors.InvalidArgumentError raised by OP_REQUIRES."""
+
+
+class CloudAAENativeError(RuntimeError):
+    """A C-ABI entry point returned a non-zero status."""
+
+
+# name -> argtypes (every entry point returns int status unless listed in _SPECIAL)
+_SIGNATURES = {
+    "caae_fps": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr],
+    "caae_fps_gather": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "caae_gather": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr],
+    "caae_gather_grad": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr],
+    "caae_prob_sample": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "caae_nn_distance": [_int, _int, _ptr, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "caae_nn_distance_grad": [_int, _int, _ptr, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+}
+_SPECIAL = {
+    "caae_abi_version": ([], _int),
+    "caae_status_string": ([_int], ctypes.c_char_p),
+    "caae_fps_scratch_bytes": ([_int, _int], ctypes.c_size_t),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(list(_SIGNATURES) + list(_SPECIAL)))
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the native library once; raise loudly when it is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the sm_100a kernels are not built. Run `python -c 'import "
+            f"__graft_entry__ as g; g.build()'` or `make -C cloudaae_b200/csrc`. There is no CPU fallback.")
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.argtypes = argtypes
+        fn.restype = _int
+    for name, (argtypes, restype) in _SPECIAL.items():
+        fn = getattr(handle, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    got = handle.caae_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI version {got}, expected {ABI_VERSION}: rebuild it")
+    _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().caae_status_string(status).decode()
+        raise CloudAAENativeError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise NotImplementedError(
+            f"{name}: cloudaae_b200 ops run on CUDA (sm_100a) tensors only; there is no CPU kernel")

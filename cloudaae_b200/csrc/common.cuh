@@ -1,0 +1,30 @@
+// common.cuh — shared helpers for the sm_100a kernels of libcloudaae_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/cloudaae_b200.h"
+
+#define CAAE_RETURN_IF(cond, code) \
+  do { if (cond) return (code); } while (0)
+
+// Launch epilogue: report the launch error (if any) as the positive cudaError_t.
+#define CAAE_LAUNCH_STATUS() ((int)cudaPeekAtLastError())
+
+namespace caae {
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+
+// The reference's squared distance in the exact operation order nvcc emits for it
+// (tf_nndistance_g.cu:30-33, tf_sampling_g.cu:141): mul.f32 y; fma.rn x; fma.rn z.
+// Spelled with intrinsics so no compiler version can re-associate or re-contract it.
+__device__ __forceinline__ float sqdist_ref(float cx, float cy, float cz, float qx, float qy, float qz) {
+  const float dx = __fsub_rn(cx, qx), dy = __fsub_rn(cy, qy), dz = __fsub_rn(cz, qz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+inline cudaStream_t as_stream(caae_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace caae

@@ -1,0 +1,244 @@
+// nn_distance.cu — chamfer nearest-neighbour distance, forward and backward, for sm_100a.
+//
+// Replaces NmDistanceKernel / NmDistanceGradKernel and their launchers
+// (reference tf_ops/nn_distance/tf_nndistance_g.cu:5-157).
+//
+// Forward.  One launch covers both directions (blockIdx.z) and every cloud (blockIdx.y); the
+// reference needs two launches of a fixed (32,16) grid in which most CTAs only stage tiles.
+// A CTA owns 128*Q queries in registers and streams the opposite cloud through a 24 KB shared
+// tile kept in the input's own AoS layout, read back as three broadcast LDS.128 per four
+// candidates.  The distance uses the reference's exact operation order (common.cuh:sqdist_ref) and
+// candidates are visited in ascending index with a strict `<`, so the argmin is the FIRST minimum —
+// bit-identical to the reference's within-tile `<` / across-tile `>` rule.
+//
+// Backward.  grid (2, b): CTA (0,i) produces grad_xyz1[i], CTA (1,i) produces grad_xyz2[i],
+// accumulating in shared memory: own terms are plain stores, cross terms shared-memory atomics,
+// then one coalesced write.  No memset, no global atomics, one launch (the reference: two memsets
+// plus two launches whose batch loop is serial inside the grid).  Clouds too large for shared
+// memory take a global-atomic path.
+#include "common.cuh"
+
+namespace caae {
+
+constexpr int kNndThreads = 128;
+constexpr int kNndTile = 2048;  // candidates per shared-memory tile (24 KB)
+
+template <int Q>
+__global__ void __launch_bounds__(kNndThreads)
+nn_distance_fwd_kernel(int n, const float* __restrict__ xyz1, int m, const float* __restrict__ xyz2,
+                       float* __restrict__ dist1, int* __restrict__ idx1, float* __restrict__ dist2,
+                       int* __restrict__ idx2) {
+  __shared__ __align__(16) float tile[kNndTile * 3];
+
+  const int cloud = blockIdx.y;
+  const bool fwd = (blockIdx.z == 0);
+  const int nq = fwd ? n : m;  // queries
+  const int nc = fwd ? m : n;  // candidates
+  const int q0 = blockIdx.x * (kNndThreads * Q);
+  if (q0 >= nq) return;  // uniform for the CTA (grid.x is sized for max(n, m))
+
+  const float* __restrict__ qp = (fwd ? xyz1 : xyz2) + (size_t)cloud * nq * 3;
+  const float* __restrict__ cp = (fwd ? xyz2 : xyz1) + (size_t)cloud * nc * 3;
+  float* __restrict__ dout = (fwd ? dist1 : dist2) + (size_t)cloud * nq;
+  int* __restrict__ iout = (fwd ? idx1 : idx2) + (size_t)cloud * nq;
+
+  const int tid = threadIdx.x;
+  float qx[Q], qy[Q], qz[Q], best[Q];
+  int besti[Q];
+#pragma unroll
+  for (int r = 0; r < Q; ++r) {
+    const int q = q0 + r * kNndThreads + tid;
+    const bool ok = q < nq;
+    qx[r] = ok ? qp[q * 3 + 0] : 0.f;
+    qy[r] = ok ? qp[q * 3 + 1] : 0.f;
+    qz[r] = ok ? qp[q * 3 + 2] : 0.f;
+    best[r] = (nc > 0) ? __int_as_float(0x7f800000) : 0.f;  // +inf; empty cloud -> (0, 0) like the CPU op
+    besti[r] = 0;
+  }
+
+  for (int c0 = 0; c0 < nc; c0 += kNndTile) {
+    const int cnt = min(kNndTile, nc - c0);
+    const float* __restrict__ src = cp + (size_t)c0 * 3;
+    if (c0 > 0) __syncthreads();  // previous tile fully consumed
+    const int nfl = cnt * 3;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const int nv = nfl >> 2;
+      const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
+      float4* tile4 = reinterpret_cast<float4*>(tile);
+      for (int i = tid; i < nv; i += kNndThreads) tile4[i] = __ldg(src4 + i);
+      for (int i = (nv << 2) + tid; i < nfl; i += kNndThreads) tile[i] = __ldg(src + i);
+    } else {
+      for (int i = tid; i < nfl; i += kNndThreads) tile[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    const int cnt4 = cnt & ~3;
+    const float4* tile4 = reinterpret_cast<const float4*>(tile);
+#pragma unroll 2
+    for (int k = 0; k < cnt4; k += 4) {
+      // 4 candidates = 12 floats: x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3
+      const float4 a = tile4[(k >> 2) * 3 + 0];
+      const float4 b = tile4[(k >> 2) * 3 + 1];
+      const float4 c = tile4[(k >> 2) * 3 + 2];
+      const int kk = c0 + k;
+#pragma unroll
+      for (int r = 0; r < Q; ++r) {
+        const float d0 = sqdist_ref(a.x, a.y, a.z, qx[r], qy[r], qz[r]);
+        const float d1 = sqdist_ref(a.w, b.x, b.y, qx[r], qy[r], qz[r]);
+        const float d2 = sqdist_ref(b.z, b.w, c.x, qx[r], qy[r], qz[r]);
+        const float d3 = sqdist_ref(c.y, c.z, c.w, qx[r], qy[r], qz[r]);
+        if (d0 < best[r]) { best[r] = d0; besti[r] = kk; }
+        if (d1 < best[r]) { best[r] = d1; besti[r] = kk + 1; }
+        if (d2 < best[r]) { best[r] = d2; besti[r] = kk + 2; }
+        if (d3 < best[r]) { best[r] = d3; besti[r] = kk + 3; }
+      }
+    }
+    for (int k = cnt4; k < cnt; ++k) {
+      const float cx = tile[k * 3 + 0], cy = tile[k * 3 + 1], cz = tile[k * 3 + 2];
+#pragma unroll
+      for (int r = 0; r < Q; ++r) {
+        const float d = sqdist_ref(cx, cy, cz, qx[r], qy[r], qz[r]);
+        if (d < best[r]) { best[r] = d; besti[r] = c0 + k; }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < Q; ++r) {
+    const int q = q0 + r * kNndThreads + tid;
+    if (q < nq) {
+      dout[q] = best[r];
+      iout[q] = besti[r];
+    }
+  }
+}
+
+// ---- backward ----------------------------------------------------------------------------------
+constexpr int kNndBwdThreads = 512;
+
+__global__ void __launch_bounds__(kNndBwdThreads)
+nn_distance_bwd_smem_kernel(int n, const float* __restrict__ xyz1, int m, const float* __restrict__ xyz2,
+                            const float* __restrict__ gd1, const int* __restrict__ idx1,
+                            const float* __restrict__ gd2, const int* __restrict__ idx2,
+                            float* __restrict__ gx1, float* __restrict__ gx2) {
+  extern __shared__ float acc[];  // nA*3
+  const int cloud = blockIdx.y;
+  const bool first = (blockIdx.x == 0);
+  const int nA = first ? n : m, nB = first ? m : n;
+  const float* __restrict__ A = (first ? xyz1 : xyz2) + (size_t)cloud * nA * 3;
+  const float* __restrict__ B = (first ? xyz2 : xyz1) + (size_t)cloud * nB * 3;
+  const float* __restrict__ gdA = (first ? gd1 : gd2) + (size_t)cloud * nA;
+  const float* __restrict__ gdB = (first ? gd2 : gd1) + (size_t)cloud * nB;
+  const int* __restrict__ idxA = (first ? idx1 : idx2) + (size_t)cloud * nA;
+  const int* __restrict__ idxB = (first ? idx2 : idx1) + (size_t)cloud * nB;
+  float* __restrict__ out = (first ? gx1 : gx2) + (size_t)cloud * nA * 3;
+
+  // own terms: g*(a_j - b_{idxA[j]}), single writer per slot
+  for (int j = threadIdx.x; j < nA; j += kNndBwdThreads) {
+    const int j2 = idxA[j];
+    const float g = __fadd_rn(gdA[j], gdA[j]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      acc[j * 3 + c] = __fmul_rn(__fsub_rn(A[j * 3 + c], B[j2 * 3 + c]), g);
+  }
+  __syncthreads();
+  // cross terms: -(g*(b_j - a_{idxB[j]})) lands on a_{idxB[j]}
+  for (int j = threadIdx.x; j < nB; j += kNndBwdThreads) {
+    const int j2 = idxB[j];
+    const float g = __fadd_rn(gdB[j], gdB[j]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      atomicAdd(&acc[j2 * 3 + c], -__fmul_rn(__fsub_rn(B[j * 3 + c], A[j2 * 3 + c]), g));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nA * 3; i += kNndBwdThreads) out[i] = acc[i];
+}
+
+// Large-cloud path: same arithmetic as the reference kernel, one direction per blockIdx.z.
+__global__ void __launch_bounds__(256)
+nn_distance_bwd_global_kernel(int n, const float* __restrict__ xyz1, int m, const float* __restrict__ xyz2,
+                              const float* __restrict__ gd1, const int* __restrict__ idx1,
+                              const float* __restrict__ gd2, const int* __restrict__ idx2,
+                              float* __restrict__ gx1, float* __restrict__ gx2) {
+  const int cloud = blockIdx.y;
+  const bool first = (blockIdx.z == 0);
+  const int nA = first ? n : m, nB = first ? m : n;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nA) return;
+  const float* __restrict__ A = (first ? xyz1 : xyz2) + (size_t)cloud * nA * 3;
+  const float* __restrict__ B = (first ? xyz2 : xyz1) + (size_t)cloud * nB * 3;
+  float* __restrict__ gA = (first ? gx1 : gx2) + (size_t)cloud * nA * 3;
+  float* __restrict__ gB = (first ? gx2 : gx1) + (size_t)cloud * nB * 3;
+  const float gdv = ((first ? gd1 : gd2) + (size_t)cloud * nA)[j];
+  const int j2 = ((first ? idx1 : idx2) + (size_t)cloud * nA)[j];
+  const float g = __fadd_rn(gdv, gdv);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fmul_rn(__fsub_rn(A[j * 3 + c], B[j2 * 3 + c]), g);
+    atomicAdd(&gA[j * 3 + c], v);
+    atomicAdd(&gB[j2 * 3 + c], -v);
+  }
+}
+
+}  // namespace caae
+
+using namespace caae;
+
+extern "C" int caae_nn_distance(int b, int n, const float* xyz, int m, const float* xyz2, float* result,
+                                int* result_i, float* result2, int* result2_i, caae_stream_t stream) {
+  CAAE_RETURN_IF(b < 0 || n < 0 || m < 0, CAAE_E_BADSHAPE);
+  CAAE_RETURN_IF(b > 65535, CAAE_E_BADSHAPE);
+  if (b == 0 || (n == 0 && m == 0)) return CAAE_OK;
+  CAAE_RETURN_IF((n > 0 && (!xyz || !result || !result_i)) || (m > 0 && (!xyz2 || !result2 || !result2_i)),
+                 CAAE_E_NULLPTR);
+  const int big = n > m ? n : m;
+  // Q = queries per thread.  Prefer 4 (fewest shared-memory reads per pair) once the grid still
+  // covers every SM at least twice; otherwise trade it for more CTAs.
+  const long ctas4 = (long)((n + 511) / 512 + (m + 511) / 512) * b;
+  const long ctas2 = (long)((n + 255) / 256 + (m + 255) / 256) * b;
+  cudaStream_t s = as_stream(stream);
+  if (ctas4 >= 2 * kNumSMs) {
+    dim3 grid((big + 511) / 512, b, 2);
+    nn_distance_fwd_kernel<4><<<grid, kNndThreads, 0, s>>>(n, xyz, m, xyz2, result, result_i, result2, result2_i);
+  } else if (ctas2 >= 2 * kNumSMs) {
+    dim3 grid((big + 255) / 256, b, 2);
+    nn_distance_fwd_kernel<2><<<grid, kNndThreads, 0, s>>>(n, xyz, m, xyz2, result, result_i, result2, result2_i);
+  } else {
+    dim3 grid((big + 127) / 128, b, 2);
+    nn_distance_fwd_kernel<1><<<grid, kNndThreads, 0, s>>>(n, xyz, m, xyz2, result, result_i, result2, result2_i);
+  }
+  return CAAE_LAUNCH_STATUS();
+}
+
+extern "C" int caae_nn_distance_grad(int b, int n, const float* xyz1, int m, const float* xyz2,
+                                     const float* grad_dist1, const int* idx1, const float* grad_dist2,
+                                     const int* idx2, float* grad_xyz1, float* grad_xyz2, caae_stream_t stream) {
+  CAAE_RETURN_IF(b < 0 || n < 0 || m < 0, CAAE_E_BADSHAPE);
+  CAAE_RETURN_IF(b > 65535, CAAE_E_BADSHAPE);
+  if (b == 0 || (n == 0 && m == 0)) return CAAE_OK;
+  cudaStream_t s = as_stream(stream);
+  if (n == 0 || m == 0) {  // no pairs: gradients are zero
+    if (n > 0) { CAAE_RETURN_IF(!grad_xyz1, CAAE_E_NULLPTR); cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * (size_t)b * n * 3, s); }
+    if (m > 0) { CAAE_RETURN_IF(!grad_xyz2, CAAE_E_NULLPTR); cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * (size_t)b * m * 3, s); }
+    return CAAE_LAUNCH_STATUS();
+  }
+  CAAE_RETURN_IF(!xyz1 || !xyz2 || !grad_dist1 || !idx1 || !grad_dist2 || !idx2 || !grad_xyz1 || !grad_xyz2,
+                 CAAE_E_NULLPTR);
+  const int big = n > m ? n : m;
+  const size_t smem = sizeof(float) * 3 * (size_t)big;
+  if (smem <= 200 * 1024) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(nn_distance_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    nn_distance_bwd_smem_kernel<<<dim3(2, b), kNndBwdThreads, smem, s>>>(n, xyz1, m, xyz2, grad_dist1, idx1,
+                                                                        grad_dist2, idx2, grad_xyz1, grad_xyz2);
+  } else {
+    cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * (size_t)b * n * 3, s);
+    cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * (size_t)b * m * 3, s);
+    nn_distance_bwd_global_kernel<<<dim3((big + 255) / 256, b, 2), 256, 0, s>>>(
+        n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2);
+  }
+  return CAAE_LAUNCH_STATUS();
+}

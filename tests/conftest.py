@@ -1,0 +1,24 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.dirname(os.path.abspath(__file__))):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_ops():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ops_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def have_reference_tree():
+    return os.path.isdir("/root/reference/tf_ops")

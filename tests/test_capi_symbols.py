@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/*.h declares."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = open(h).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"\b(caae_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_header_declares_the_hot_path_entry_points():
+    names = _declared_symbols()
+    for required in ("caae_fps", "caae_gather", "caae_gather_grad", "caae_nn_distance", "caae_nn_distance_grad",
+                     "caae_prob_sample"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    from cloudaae_b200 import _capi
+    lib = _capi.lib()  # raises loudly when the .so is missing
+    handle = ctypes.CDLL(_capi.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(handle, name), f"{name} declared in include/ but not exported"
+    assert lib.caae_abi_version() == _capi.ABI_VERSION
+    assert set(_capi.EXPORTED_SYMBOLS) <= set(_declared_symbols())
+
+
+def test_status_strings_and_argument_errors_need_no_gpu():
+    from cloudaae_b200 import _capi
+    lib = _capi.lib()
+    assert lib.caae_status_string(0) == b"ok"
+    assert b"scratch" in lib.caae_status_string(-3)
+    # argument validation happens before any CUDA call
+    assert lib.caae_nn_distance(-1, 1, None, 1, None, None, None, None, None, None) == -1
+    assert lib.caae_nn_distance(1, 4, None, 4, None, None, None, None, None, None) == -2
+    assert lib.caae_fps(1, 0, 4, None, None, None, None) == -1
+    assert lib.caae_fps(0, 0, 4, None, None, None, None) == 0
+    assert lib.caae_fps_scratch_bytes(4, 2048) == 0
+    assert lib.caae_fps_scratch_bytes(4, 10000) == 4 * 10000 * 4
+    with pytest.raises(_capi.CloudAAENativeError, match="null pointer"):
+        _capi.check(-2, "x")
+
+
+def test_product_package_never_imports_the_oracle():
+    """The product path must not route through oracle/ (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "cloudaae_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "caae_oracle" not in text and "libcloudaae_ref" not in text, f
