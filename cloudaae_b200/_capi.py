@@ -27,20 +27,52 @@ class CloudAAENativeError(RuntimeError):
     """A C-ABI entry point returned a non-zero status."""
 
 
-# name -> argtypes (every entry point returns int status unless listed in _SPECIAL)
+# name -> argument codes (i = int, l = long, f = float, d = double, p = pointer / stream handle).
+# Every entry point returns an int status unless listed in _SPECIAL.
+_CODES = {"i": _int, "l": ctypes.c_long, "f": ctypes.c_float, "d": ctypes.c_double, "p": _ptr}
 _SIGNATURES = {
-    "caae_fps": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr],
-    "caae_fps_gather": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr],
-    "caae_gather": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr],
-    "caae_gather_grad": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr],
-    "caae_prob_sample": [_int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr],
-    "caae_nn_distance": [_int, _int, _ptr, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
-    "caae_nn_distance_grad": [_int, _int, _ptr, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    # tf_ops drop-ins
+    "caae_fps": "iiipppp",
+    "caae_fps_gather": "iiippppp",
+    "caae_gather": "iiipppp",
+    "caae_gather_grad": "iiipppp",
+    "caae_prob_sample": "iiippppp",
+    "caae_nn_distance": "iipippppp" "p",
+    "caae_nn_distance_grad": "iipippppppp" "p",
+    # model building blocks
+    "caae_gemm_f32": "iiiiipipipipi" "p",
+    "caae_knn": "iiiipip" "p",
+    "caae_edge_stats": "iiiipipp" "p",
+    "caae_edge_apply": "iiiipippppi" "p",
+    "caae_edge_bwd_reduce": "iiiipippppppip" "p",
+    "caae_edge_bwd_apply": "iiiipipppppppipi" "p",
+    "caae_col_stats": "iipip" "p",
+    "caae_bn_finalize": "ipidppppppppp" "p",
+    "caae_bn_eval_coeffs": "ippppp" "pp",
+    "caae_bn_bwd_finalize": "ipidppppp" "p",
+    "caae_bn_act": "iipippipi" "p",
+    "caae_bn_act_pool": "iiipippipp" "p",
+    "caae_bn_act_bwd_reduce": "iipipppppiifipp" "p",
+    "caae_bn_act_bwd_apply": "iipippppppiifippi" "p",
+    "caae_colsum": "iipip" "p",
+    "caae_edge_fold_weights": "iippppi" "p",
+    "caae_edge_unfold_wgrad": "iipip" "p",
+    # losses / optimiser / step state
+    "caae_pose_losses": "ipppppffppppp" "p",
+    "caae_loss_reduce": "lppippp" "p",
+    "caae_add_cloud_vec": "iippp" "p",
+    "caae_prepare_input": "iiipppipp" "p",
+    "caae_step_begin": "pi" "p",
+    "caae_adam_tf": "lpppppfffff" "p",
+    "caae_fill_f32": "lpf" "p",
 }
+_SIGNATURES = {k: [_CODES[c] for c in v] for k, v in _SIGNATURES.items()}
 _SPECIAL = {
     "caae_abi_version": ([], _int),
     "caae_status_string": ([_int], ctypes.c_char_p),
     "caae_fps_scratch_bytes": ([_int, _int], ctypes.c_size_t),
+    "caae_edge_parts": ([_int, _int], _int),
+    "caae_col_parts": ([_int], _int),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(list(_SIGNATURES) + list(_SPECIAL)))

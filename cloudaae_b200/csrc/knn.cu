@@ -1,0 +1,161 @@
+// knn.cu — fused pairwise distance + top-k neighbour selection (never materialises [B,N,N]).
+//
+// Replaces pairwise_xyz_distance + knn (reference utils/tf_util.py:597-632: batched matmul into a
+// [B,N,N] tensor, then tf.nn.top_k).  Same metric — D(i,j) = (|x_i|^2 + (-2 x_i.x_j)) + |x_j|^2 in
+// fp32 FFMA arithmetic (not TF32: neighbour sets must be stable) — and the same selection: the k
+// smallest, ascending, ties to the lower index, the point itself included.
+//
+// Layout.  x is [B*N, ldx] row-major; the first `c` channels of a row are the feature (c = 3 for
+// layer 1, 64 for layers 2-4, read in place from the 320-wide concat buffer).
+// Mapping.  A CTA owns 64 query rows of one cloud; warp w owns 8 of them; candidates stream
+// through shared memory in chunks of 256, stored channel-major so lane l reads its 8 candidates
+// (256*chunk + 8l ..) as two LDS.128 and the 8 query values as two broadcast LDS.128: 64 FFMA per
+// 4 LDS.  Selection is k rounds of "lane-local min, REDUX min over the warp, REDUX min over the
+// matching indices", merged across chunks through a k-entry list per row.
+#include "common.cuh"
+
+namespace caae {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_QROWS = 64;     // query rows per CTA
+constexpr int KNN_CHUNK = 256;    // candidates per shared-memory chunk
+constexpr int KNN_XT_LD = KNN_CHUNK + 4;
+constexpr int KNN_QT_LD = KNN_QROWS + 4;
+constexpr int KNN_MAXK = 32;
+
+__device__ __forceinline__ uint32_t sortable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __restrict__ idx_out) {
+  extern __shared__ __align__(16) float smem[];
+  float* XT = smem;                               // [c][KNN_XT_LD]
+  float* QT = XT + (size_t)c * KNN_XT_LD;         // [c][KNN_QT_LD]
+  float* sqc = QT + (size_t)c * KNN_QT_LD;        // [KNN_CHUNK]
+  float* sqq = sqc + KNN_CHUNK;                   // [KNN_QROWS]
+  uint32_t* lkey = reinterpret_cast<uint32_t*>(sqq + KNN_QROWS);  // [KNN_QROWS][KNN_MAXK]
+  int* lidx = reinterpret_cast<int*>(lkey + KNN_QROWS * KNN_MAXK);
+
+  const int cloud = blockIdx.y;
+  const int q0 = blockIdx.x * KNN_QROWS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ xc = x + (size_t)cloud * n * ldx;
+
+  // ---- stage the query rows (channel-major) and their squared norms
+  for (int e = tid; e < KNN_QROWS * c; e += KNN_THREADS) {
+    const int r = e / c, ch = e - r * c;
+    const int q = q0 + r;
+    QT[ch * KNN_QT_LD + r] = (q < n) ? __ldg(xc + (size_t)q * ldx + ch) : 0.f;
+  }
+  for (int e = tid; e < KNN_QROWS * KNN_MAXK; e += KNN_THREADS) { lkey[e] = 0xffffffffu; lidx[e] = 0x7fffffff; }
+  __syncthreads();
+  if (tid < KNN_QROWS) {
+    float s = 0.f;
+    for (int ch = 0; ch < c; ++ch) { const float v = QT[ch * KNN_QT_LD + tid]; s = fmaf(v, v, s); }
+    sqq[tid] = s;
+  }
+
+  for (int j0 = 0; j0 < n; j0 += KNN_CHUNK) {
+    __syncthreads();  // previous chunk consumed (and sqq visible on the first pass)
+    for (int e = tid; e < KNN_CHUNK * c; e += KNN_THREADS) {
+      const int r = e / c, ch = e - r * c;
+      const int j = j0 + r;
+      XT[ch * KNN_XT_LD + r] = (j < n) ? __ldg(xc + (size_t)j * ldx + ch) : 0.f;
+    }
+    __syncthreads();
+    {
+      float s = 0.f;
+      for (int ch = 0; ch < c; ++ch) { const float v = XT[ch * KNN_XT_LD + tid]; s = fmaf(v, v, s); }
+      sqc[tid] = s;  // KNN_THREADS == KNN_CHUNK
+    }
+    __syncthreads();
+
+    // ---- 8 rows x 8 candidates of dot products per lane
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int ch = 0; ch < c; ++ch) {
+      const float4 a0 = *reinterpret_cast<const float4*>(QT + ch * KNN_QT_LD + warp * 8);
+      const float4 a1 = *reinterpret_cast<const float4*>(QT + ch * KNN_QT_LD + warp * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(XT + ch * KNN_XT_LD + lane * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(XT + ch * KNN_XT_LD + lane * 8 + 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+
+    // ---- selection, one row at a time (the whole warp works on the same row)
+    float sj[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sj[j] = sqc[lane * 8 + j];
+    const int jbase = j0 + lane * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = warp * 8 + i;
+      const float si = sqq[row];
+      uint32_t key[9];
+      int cidx[9];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = __fadd_rn(__fadd_rn(si, __fmul_rn(-2.f, acc[i][j])), sj[j]);
+        const bool ok = (jbase + j) < n;
+        key[j] = ok ? sortable(d) : 0xffffffffu;
+        cidx[j] = ok ? (jbase + j) : 0x7fffffff;
+      }
+      // 9th slot: the row's running list from earlier chunks (lane l holds entry l)
+      key[8] = (lane < k) ? lkey[row * KNN_MAXK + lane] : 0xffffffffu;
+      cidx[8] = (lane < k) ? lidx[row * KNN_MAXK + lane] : 0x7fffffff;
+      __syncwarp();
+      for (int r = 0; r < k; ++r) {
+        uint32_t lmin = key[0];
+#pragma unroll
+        for (int j = 1; j < 9; ++j) lmin = min(lmin, key[j]);
+        const uint32_t wmin = __reduce_min_sync(0xffffffffu, lmin);
+        int lcand = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) lcand = (key[j] == wmin) ? min(lcand, cidx[j]) : lcand;
+        const int widx = __reduce_min_sync(0xffffffffu, lcand);
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          if (cidx[j] == widx) { key[j] = 0xffffffffu; cidx[j] = 0x7fffffff; }
+        if (lane == r) { lkey[row * KNN_MAXK + r] = wmin; lidx[row * KNN_MAXK + r] = widx; }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < KNN_QROWS * k; e += KNN_THREADS) {
+    const int r = e / k, s = e - r * k;
+    const int q = q0 + r;
+    if (q < n) idx_out[((size_t)cloud * n + q) * k + s] = lidx[r * KNN_MAXK + s];
+  }
+}
+
+}  // namespace caae
+
+using namespace caae;
+
+extern "C" int caae_knn(int b, int n, int c, int k, const float* x, int ldx, int* idx, caae_stream_t stream) {
+  CAAE_RETURN_IF(b < 0 || n < 0 || c <= 0 || k <= 0 || ldx < c, CAAE_E_BADSHAPE);
+  CAAE_RETURN_IF(k > KNN_MAXK || k > n, CAAE_E_BADSHAPE);  // tf.nn.top_k also rejects k > N
+  if (b == 0 || n == 0) return CAAE_OK;
+  CAAE_RETURN_IF(!x || !idx, CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(b > 65535, CAAE_E_BADSHAPE);
+  const size_t smem = sizeof(float) * ((size_t)c * (KNN_XT_LD + KNN_QT_LD) + KNN_CHUNK + KNN_QROWS) +
+                      sizeof(int) * 2 * KNN_QROWS * KNN_MAXK;
+  CAAE_RETURN_IF(smem > 220 * 1024, CAAE_E_UNSUPPORTED);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid((n + KNN_QROWS - 1) / KNN_QROWS, b);
+  knn_kernel<<<grid, KNN_THREADS, smem, as_stream(stream)>>>(n, c, k, x, ldx, idx);
+  return CAAE_LAUNCH_STATUS();
+}

@@ -1,0 +1,483 @@
+"""CloudAAE networks — drop-in for the reference's ``models/pointnet_ycb_23_decoder_4.py``.
+
+``get_model_dgcnn_mean_6d(point_cloud, is_training_pl_encoder, is_training, k_neighbor, bn_decay=None)``
+(:327-455, the network both reference scripts run) and ``get_model_pn(point_cloud, is_training,
+bn_decay=None)`` (:23-89) keep the reference's names, argument order and return tuple
+``(net_recon, net_rot, net_trans, end_points)``.  Tensors are torch CUDA tensors; every layer runs on
+the hand-written sm_100a kernels behind the ``caae_*`` C ABI (no torch.nn, no cuBLAS on this path).
+
+TensorFlow keeps variables in named scopes of a graph; here a :class:`Variables` store plays that
+role (same names: ``dgcnn1/weights``, ``dgcnn_agg/bn/gamma`` ...), holding all trainable parameters
+in ONE flat fp32 buffer — the operand of the fused Adam kernel and of the data-parallel allreduce.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from .. import _capi
+
+NUM_CLASS = 21
+_ALIGN = 32  # floats; every parameter tensor starts on a 128-byte boundary
+
+# (scope, fan_in, fan_out, has_bn) in the reference's creation order
+DGCNN_LAYERS = [
+    ("dgcnn1", 48, 64, True), ("dgcnn2", 128, 64, True), ("dgcnn3", 128, 64, True), ("dgcnn4", 128, 128, True),
+    ("dgcnn_agg", 320, 1024, True), ("dgcnn_fc1", 1024, 1024, True), ("dgcnn_fc2", 1024, 1024, True),
+    ("dgcnn_output", 1024, 3072, False),
+    ("dgcnn_rot_fc1", 1024, 512, True), ("dgcnn_rot_fc2", 512, 256, True), ("dgcnn_output_rot", 256, 3, False),
+    ("dgcnn_trans_fc1", 1024, 512, True), ("dgcnn_trans_fc2", 512, 256, True), ("dgcnn_output_trans", 256, 3, False),
+]
+
+
+def dgcnn_layers(num_point: int = 256, point_dim: int = 24):
+    layers = list(DGCNN_LAYERS)
+    layers[0] = ("dgcnn1", 2 * point_dim, 64, True)
+    layers[7] = ("dgcnn_output", 1024, num_point * 12, False)
+    return layers
+
+
+def pn_layers(num_point: int = 256, point_dim: int = 24):
+    return [
+        ("pn_conv1_encoder", point_dim, 64, True), ("pn_conv2_encoder", 64, 64, True),
+        ("pn_conv3_encoder", 64, 64, True), ("pn_conv4_encoder", 64, 128, True), ("pn_conv5_encoder", 128, 1024, True),
+        ("pn_fc1_decoder", 1024, 1024, True), ("pn_fc2_decoder", 1024, 1024, True),
+        ("pn_output", 1024, num_point * 12, False),
+        ("pn_rot_fc1", 1024, 512, True), ("pn_rot_fc2", 512, 256, True), ("pn_output_rot", 256, 3, False),
+        ("pn_trans_fc1", 1024, 512, True), ("pn_trans_fc2", 512, 256, True), ("pn_output_trans", 256, 3, False),
+    ]
+
+
+class Variables:
+    """Named parameter store over flat buffers (the analogue of TF variable scopes + Saver).
+
+    ``flat``/``grad``: all trainable parameters / their gradients (weights, biases, bn/beta, bn/gamma),
+    ``ema``: the non-trainable moving averages (bn/ema_mean, bn/ema_var; start at 0 like TF's
+    ExponentialMovingAverage shadows of tensors).  Initialisation follows utils/tf_util.py:42-43
+    (Xavier-uniform weights), :164-165 (zero biases) and :488-491 (gamma 1, beta 0).
+    """
+
+    def __init__(self, layers, device="cuda", seed: int | None = 0):
+        self.layers = list(layers)
+        self.device = torch.device(device)
+        self.index = OrderedDict()
+        self.ema_index = OrderedDict()
+        off = eoff = 0
+
+        def _add(table, name, shape, o):
+            table[name] = (o, tuple(shape))
+            return o + ((math.prod(shape) + _ALIGN - 1) // _ALIGN) * _ALIGN
+
+        for scope, fin, fout, has_bn in self.layers:
+            off = _add(self.index, f"{scope}/weights", (fin, fout), off)
+            off = _add(self.index, f"{scope}/biases", (fout,), off)
+            if has_bn:
+                off = _add(self.index, f"{scope}/bn/beta", (fout,), off)
+                off = _add(self.index, f"{scope}/bn/gamma", (fout,), off)
+                eoff = _add(self.ema_index, f"{scope}/bn/ema_mean", (fout,), eoff)
+                eoff = _add(self.ema_index, f"{scope}/bn/ema_var", (fout,), eoff)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.ema = torch.zeros(max(eoff, 1), dtype=torch.float32, device=self.device)
+        self.num_trainable = sum(math.prod(s) for _, s in self.index.values())
+        if seed is not None:
+            self.initialize(seed)
+
+    # -- access
+    def _view(self, buf, table, name):
+        o, shape = table[name]
+        return buf[o:o + math.prod(shape)].view(shape)
+
+    def __getitem__(self, name):
+        if name in self.index:
+            return self._view(self.flat, self.index, name)
+        return self._view(self.ema, self.ema_index, name)
+
+    def __contains__(self, name):
+        return name in self.index or name in self.ema_index
+
+    def grad_of(self, name):
+        return self._view(self.grad, self.index, name)
+
+    def names(self):
+        return list(self.index) + list(self.ema_index)
+
+    def trainable_names(self):
+        return list(self.index)
+
+    # -- init / io
+    def initialize(self, seed: int):
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            self.flat.zero_(); self.ema.zero_()
+            for scope, fin, fout, has_bn in self.layers:
+                limit = math.sqrt(6.0 / (fin + fout))
+                w = (torch.rand(fin, fout, generator=g, dtype=torch.float64) * 2 - 1) * limit
+                self[f"{scope}/weights"].copy_(w.float())
+                if has_bn:
+                    self[f"{scope}/bn/gamma"].fill_(1.0)
+
+    def load_state_dict(self, state):
+        with torch.no_grad():
+            for name in self.names():
+                if name in state:
+                    self[name].copy_(torch.as_tensor(state[name]).to(torch.float32).reshape(self[name].shape))
+
+    def state_dict(self):
+        return OrderedDict((n, self[n].detach().clone()) for n in self.names())
+
+    def grads_dict(self):
+        return OrderedDict((n, self.grad_of(n).detach().clone()) for n in self.index)
+
+
+# ---------------------------------------------------------------------------------------------
+class _Engine:
+    """Forward/backward orchestration over the C ABI for one (model, B, N, k) configuration.
+
+    Workspaces are allocated once; a forward followed by its backward may be captured in a CUDA
+    graph.  Activations are [B*N, C] row-major; the four EdgeConv outputs live side by side in the
+    320-wide concat buffer ``hcat`` (no concat copy), and EdgeConv layer l reads its input features
+    from the slice layer l-1 wrote.
+    """
+
+    def __init__(self, variables: Variables, model: str, batch: int, num_point: int, point_dim: int, k: int = 10):
+        self.v = variables
+        self.model = model
+        self.B, self.N, self.D, self.k = batch, num_point, point_dim, k
+        self.R = batch * num_point
+        self.dev = variables.device
+        self.lib = _capi.lib()
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        R, B = self.R, self.B
+        self.scopes = {s: (fin, fout, bn) for s, fin, fout, bn in variables.layers}
+        self.bn = {}
+        for s, (fin, fout, bn) in self.scopes.items():
+            if bn:
+                self.bn[s] = {k_: torch.empty(fout, **f32) for k_ in ("scale", "shift", "mean", "invstd")}
+                self.bn[s]["coef"] = torch.empty(3 * fout, **f32)
+        nparts = max(self.lib.caae_edge_parts(B, num_point), self.lib.caae_col_parts(R), 1)
+        self.parts = torch.empty(nparts * 2 * 1024, dtype=torch.float64, device=self.dev)
+        self.default_decay = torch.full((1,), 0.9, **f32)  # tf_util.py:494: decay defaults to 0.9
+        self.decay_scalar = torch.empty(1, **f32)
+        self.emb = torch.empty(B, 1024, **f32)
+        self.d_emb = torch.empty(B, 1024, **f32)
+        if model == "dgcnn":
+            self.cins = [point_dim, 64, 64, 64]
+            self.couts = [64, 64, 64, 128]
+            self.offs = [0, 64, 128, 192]
+            self.hcat = torch.empty(R, 320, **f32)
+            self.d_hcat = torch.empty(R, 320, **f32)
+            self.idx = [torch.empty(R, k, dtype=torch.int32, device=self.dev) for _ in range(4)]
+            self.pq = [torch.empty(R, 2 * c, **f32) for c in self.couts]
+            self.d_pq = torch.empty(R, 2 * max(self.couts), **f32)
+            self.wf = [torch.empty(ci, 2 * co, **f32) for ci, co in zip(self.cins, self.couts)]
+            self.bf = [torch.empty(2 * co, **f32) for co in self.couts]
+            self.d_wf = torch.empty(max(self.cins), 2 * max(self.couts), **f32)
+            self.yagg = torch.empty(R, 1024, **f32)
+        else:
+            self.enc = ["pn_conv1_encoder", "pn_conv2_encoder", "pn_conv3_encoder", "pn_conv4_encoder",
+                        "pn_conv5_encoder"]
+            self.enc_y = [torch.empty(R, self.scopes[s][1], **f32) for s in self.enc]
+            self.enc_a = [torch.empty(R, self.scopes[s][1], **f32) for s in self.enc[:-1]]
+            self.enc_d = [torch.empty(R, self.scopes[s][1], **f32) for s in self.enc[:-1]]
+            self.argmax = torch.empty(B, 1024, dtype=torch.int32, device=self.dev)
+        p = "dgcnn" if model == "dgcnn" else "pn"
+        self.prefix = p
+        fc1, fc2, out = (f"{p}_fc1", f"{p}_fc2", f"{p}_output") if p == "dgcnn" else \
+            ("pn_fc1_decoder", "pn_fc2_decoder", "pn_output")
+        self.branches = [[fc1, fc2, out], [f"{p}_rot_fc1", f"{p}_rot_fc2", f"{p}_output_rot"],
+                         [f"{p}_trans_fc1", f"{p}_trans_fc2", f"{p}_output_trans"]]
+        self.fc_y, self.fc_a, self.fc_d = {}, {}, {}
+        for br in self.branches:
+            for s in br:
+                fout = self.scopes[s][1]
+                self.fc_y[s] = torch.empty(B, fout, **f32)
+                if self.scopes[s][2]:
+                    self.fc_a[s] = torch.empty(B, fout, **f32)
+                    self.fc_d[s] = torch.empty(B, fout, **f32)
+        self.x0 = None
+        self.trained = (False, False)
+
+    # -- helpers
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _c(self, name, *args):
+        _capi.check(getattr(self.lib, name)(*args, self._st()), name)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def _gemm(self, ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, acc=0):
+        self._c("caae_gemm_f32", ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), acc)
+
+    def _bn_coeffs(self, scope, training, nparts, count, decay):
+        v, bn = self.v, self.bn[scope]
+        C = self.scopes[scope][1]
+        if training:
+            self._c("caae_bn_finalize", C, self._p(self.parts), nparts, float(count), self._p(v[f"{scope}/bn/gamma"]),
+                    self._p(v[f"{scope}/bn/beta"]), self._p(v[f"{scope}/bn/ema_mean"]),
+                    self._p(v[f"{scope}/bn/ema_var"]), self._p(decay), self._p(bn["scale"]), self._p(bn["shift"]),
+                    self._p(bn["mean"]), self._p(bn["invstd"]))
+        else:
+            self._c("caae_bn_eval_coeffs", C, self._p(v[f"{scope}/bn/gamma"]), self._p(v[f"{scope}/bn/beta"]),
+                    self._p(v[f"{scope}/bn/ema_mean"]), self._p(v[f"{scope}/bn/ema_var"]), self._p(bn["scale"]),
+                    self._p(bn["shift"]))
+
+    def _dense_fwd(self, scope, x, ldx, R, training, decay, y, a):
+        """y = x W + b; (BN + ReLU -> a) when the layer has BN (tf_util.conv2d 1x1 / fully_connected)."""
+        fin, fout, has_bn = self.scopes[scope]
+        self._gemm(0, 0, R, fout, fin, x, ldx, self.v[f"{scope}/weights"], fout, y, fout, self.v[f"{scope}/biases"])
+        if has_bn:
+            if training:
+                self._c("caae_col_stats", R, fout, self._p(y), fout, self._p(self.parts))
+            self._bn_coeffs(scope, training, self.lib.caae_col_parts(R), R, decay)
+            if a is not None:
+                bn = self.bn[scope]
+                self._c("caae_bn_act", R, fout, self._p(y), fout, self._p(bn["scale"]), self._p(bn["shift"]), 1,
+                        self._p(a), fout)
+
+    def _bn_bwd(self, scope, R, y, d_out, ldo, group, gscale, argmax, d_y):
+        """training-mode BN + ReLU backward on [R, C]: d_out (per group row) -> d_y; bn/beta, bn/gamma grads."""
+        C = self.scopes[scope][1]
+        bn, v = self.bn[scope], self.v
+        self._c("caae_bn_act_bwd_reduce", R, C, self._p(y), C, self._p(bn["scale"]), self._p(bn["shift"]),
+                self._p(bn["mean"]), self._p(bn["invstd"]), self._p(d_out), ldo, group, float(gscale), 1,
+                self._p(argmax), self._p(self.parts))
+        self._c("caae_bn_bwd_finalize", C, self._p(self.parts), self.lib.caae_col_parts(R), float(R),
+                self._p(v[f"{scope}/bn/gamma"]), self._p(bn["invstd"]), self._p(bn["coef"]),
+                self._p(v.grad_of(f"{scope}/bn/gamma")), self._p(v.grad_of(f"{scope}/bn/beta")))
+        self._c("caae_bn_act_bwd_apply", R, C, self._p(y), C, self._p(bn["scale"]), self._p(bn["shift"]),
+                self._p(bn["mean"]), self._p(bn["invstd"]), self._p(bn["coef"]), self._p(d_out), ldo, group,
+                float(gscale), 1, self._p(argmax), self._p(d_y), C)
+
+    def _dense_wgrad(self, scope, x, ldx, R, d_y, bias_grad):
+        fin, fout, _ = self.scopes[scope]
+        self._gemm(1, 0, fin, fout, R, x, ldx, d_y, fout, self.v.grad_of(f"{scope}/weights"), fout)
+        if bias_grad:
+            self._c("caae_colsum", R, fout, self._p(d_y), fout, self._p(self.v.grad_of(f"{scope}/biases")))
+
+    # -- forward
+    def forward(self, x, train_enc: bool, train_fc: bool, decay=None, want_before_embedding=False):
+        """x f32[B,N,D] contiguous.  decay: 1-element device tensor (bn_decay) or None (-> 0.9)."""
+        B, N, R, D, k = self.B, self.N, self.R, self.D, self.k
+        assert x.shape == (B, N, D) and x.is_contiguous() and x.dtype == torch.float32
+        decay = self.default_decay if decay is None else decay
+        self.x0 = x
+        self.trained = (train_enc, train_fc)
+        before = None
+        if self.model == "dgcnn":
+            feat, ldf, cknn = x, D, 3
+            for l in range(4):
+                scope = f"dgcnn{l + 1}"
+                ci, co = self.cins[l], self.couts[l]
+                self._c("caae_knn", B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
+                self._c("caae_edge_fold_weights", ci, co, self._p(self.v[f"{scope}/weights"]),
+                        self._p(self.v[f"{scope}/biases"]), self._p(self.wf[l]), self._p(self.bf[l]), co)
+                self._gemm(0, 0, R, 2 * co, ci, feat, ldf, self.wf[l], 2 * co, self.pq[l], 2 * co, self.bf[l])
+                if train_enc:
+                    self._c("caae_edge_stats", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
+                            self._p(self.parts))
+                self._bn_coeffs(scope, train_enc, self.lib.caae_edge_parts(B, N), R * k, decay)
+                out = self.hcat[:, self.offs[l]:]
+                bn = self.bn[scope]
+                self._c("caae_edge_apply", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
+                        self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320)
+                feat, ldf, cknn = out, 320, co
+            scope = "dgcnn_agg"
+            self._dense_fwd(scope, self.hcat, 320, R, train_enc, decay, self.yagg, None)
+            bn = self.bn[scope]
+            self._c("caae_bn_act_pool", B, N, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]),
+                    self._p(bn["shift"]), 0, self._p(self.emb), None)
+            if want_before_embedding:
+                before = torch.empty(R, 1024, dtype=torch.float32, device=self.dev)
+                self._c("caae_bn_act", R, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]), self._p(bn["shift"]),
+                        1, self._p(before), 1024)
+        else:
+            inp, ldi = x, D
+            for i, scope in enumerate(self.enc):
+                last = i == len(self.enc) - 1
+                self._dense_fwd(scope, inp, ldi, R, train_enc, decay, self.enc_y[i], None if last else self.enc_a[i])
+                if not last:
+                    inp, ldi = self.enc_a[i], self.scopes[scope][1]
+            bn = self.bn[self.enc[-1]]
+            self._c("caae_bn_act_pool", B, N, 1024, self._p(self.enc_y[-1]), 1024, self._p(bn["scale"]),
+                    self._p(bn["shift"]), 1, self._p(self.emb), self._p(self.argmax))
+        outs = []
+        for br in self.branches:
+            inp = self.emb
+            for s in br:
+                fin, fout, has_bn = self.scopes[s]
+                self._dense_fwd(s, inp, fin, B, train_fc, decay, self.fc_y[s], self.fc_a.get(s))
+                inp = self.fc_a.get(s)
+            outs.append(self.fc_y[br[-1]])
+        return outs[0], outs[1], outs[2], self.emb, before
+
+    # -- backward (training-mode BN only, like the reference's training graph)
+    def backward(self, d_recon, d_rot, d_trans, d_emb_extra=None):
+        """Gradients of all trainable variables into ``variables.grad``.  d_* are f32 [B, fout]."""
+        assert self.trained == (True, True), "backward is defined for training-mode batch norm"
+        B, N, R, k = self.B, self.N, self.R, self.k
+        first = True
+        for br, d_out in zip(self.branches, (d_recon, d_rot, d_trans)):
+            s3, s2, s1 = br[2], br[1], br[0]
+            f3, f2, f1 = self.scopes[s3], self.scopes[s2], self.scopes[s1]
+            d_out = d_out.contiguous()
+            # linear output layer
+            self._dense_wgrad(s3, self.fc_a[s2], f3[0], B, d_out, True)
+            self._gemm(0, 1, B, f3[0], f3[1], d_out, f3[1], self.v[f"{s3}/weights"], f3[1], self.fc_d[s2], f3[0])
+            # fc2: BN+ReLU backward, wgrad, dgrad
+            self._bn_bwd(s2, B, self.fc_y[s2], self.fc_d[s2], f2[1], 1, 1.0, None, self.fc_d[s2])
+            self._dense_wgrad(s2, self.fc_a[s1], f2[0], B, self.fc_d[s2], False)
+            self._gemm(0, 1, B, f2[0], f2[1], self.fc_d[s2], f2[1], self.v[f"{s2}/weights"], f2[1], self.fc_d[s1], f2[0])
+            # fc1
+            self._bn_bwd(s1, B, self.fc_y[s1], self.fc_d[s1], f1[1], 1, 1.0, None, self.fc_d[s1])
+            self._dense_wgrad(s1, self.emb, f1[0], B, self.fc_d[s1], False)
+            self._gemm(0, 1, B, f1[0], f1[1], self.fc_d[s1], f1[1], self.v[f"{s1}/weights"], f1[1], self.d_emb, f1[0],
+                       None, 0 if first else 1)
+            first = False
+        if d_emb_extra is not None:
+            self.d_emb.add_(d_emb_extra)
+        if self.model == "dgcnn":
+            scope = "dgcnn_agg"
+            # mean-pool + ReLU + BN backward, in place over the pre-activation
+            self._bn_bwd(scope, R, self.yagg, self.d_emb, 1024, N, 1.0 / N, None, self.yagg)
+            self._dense_wgrad(scope, self.hcat, 320, R, self.yagg, False)
+            self._gemm(0, 1, R, 320, 1024, self.yagg, 1024, self.v[f"{scope}/weights"], 1024, self.d_hcat, 320)
+            for l in (3, 2, 1, 0):
+                scope = f"dgcnn{l + 1}"
+                ci, co = self.cins[l], self.couts[l]
+                bn = self.bn[scope]
+                d_out = self.d_hcat[:, self.offs[l]:]
+                args = (B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]), self._p(bn["scale"]),
+                        self._p(bn["shift"]), self._p(bn["mean"]), self._p(bn["invstd"]))
+                self._c("caae_edge_bwd_reduce", *args, self._p(d_out), 320, self._p(self.parts))
+                self._c("caae_bn_bwd_finalize", co, self._p(self.parts), self.lib.caae_edge_parts(B, N), float(R * k),
+                        self._p(self.v[f"{scope}/bn/gamma"]), self._p(bn["invstd"]), self._p(bn["coef"]),
+                        self._p(self.v.grad_of(f"{scope}/bn/gamma")), self._p(self.v.grad_of(f"{scope}/bn/beta")))
+                self._c("caae_edge_bwd_apply", *args, self._p(bn["coef"]), self._p(d_out), 320, self._p(self.d_pq),
+                        2 * co)
+                feat, ldf = (self.x0, self.D) if l == 0 else (self.hcat[:, self.offs[l - 1]:], 320)
+                # dWf = X^T dPQ, then unfold to the reference's [2C, cout] weight
+                self._gemm(1, 0, ci, 2 * co, R, feat, ldf, self.d_pq, 2 * co, self.d_wf, 2 * co)
+                self._c("caae_edge_unfold_wgrad", ci, co, self._p(self.d_wf), 2 * co,
+                        self._p(self.v.grad_of(f"{scope}/weights")))
+                if l > 0:  # d(net_{l-1}) += dPQ Wf^T, accumulated into its slice of d_hcat
+                    self._gemm(0, 1, R, ci, 2 * co, self.d_pq, 2 * co, self.wf[l], 2 * co,
+                               self.d_hcat[:, self.offs[l - 1]:], 320, None, 1)
+        else:
+            last = len(self.enc) - 1
+            scope = self.enc[last]
+            self._bn_bwd(scope, R, self.enc_y[last], self.d_emb, 1024, N, 1.0, self.argmax, self.enc_y[last])
+            d_y = self.enc_y[last]
+            for i in range(last, -1, -1):
+                scope = self.enc[i]
+                fin, fout, _ = self.scopes[scope]
+                inp, ldi = (self.x0, self.D) if i == 0 else (self.enc_a[i - 1], fin)
+                self._dense_wgrad(scope, inp, ldi, R, d_y, False)
+                if i > 0:
+                    self._gemm(0, 1, R, fin, fout, d_y, fout, self.v[f"{scope}/weights"], fout, self.enc_d[i - 1], fin)
+                    prev = self.enc[i - 1]
+                    self._bn_bwd(prev, R, self.enc_y[i - 1], self.enc_d[i - 1], fin, 1, 1.0, None, self.enc_d[i - 1])
+                    d_y = self.enc_d[i - 1]
+
+
+# ---------------------------------------------------------------------------------------------
+_DEFAULT_VARIABLES: dict = {}
+_ENGINES: dict = {}
+
+
+def get_variables(model: str, num_point: int = 256, point_dim: int = 24, device="cuda", seed: int = 0) -> Variables:
+    """The default variable store of a model (TF's default graph collection), created on first use."""
+    key = (model, num_point, point_dim, str(torch.device(device)))
+    if key not in _DEFAULT_VARIABLES:
+        layers = dgcnn_layers(num_point, point_dim) if model == "dgcnn" else pn_layers(num_point, point_dim)
+        _DEFAULT_VARIABLES[key] = Variables(layers, device=device, seed=seed)
+    return _DEFAULT_VARIABLES[key]
+
+
+def reset_default_variables():
+    _DEFAULT_VARIABLES.clear()
+    _ENGINES.clear()
+
+
+def _engine_for(variables: Variables, model: str, b: int, n: int, d: int, k: int) -> _Engine:
+    key = (id(variables), model, b, n, d, k)
+    if key not in _ENGINES:
+        _ENGINES[key] = _Engine(variables, model, b, n, d, k)
+    return _ENGINES[key]
+
+
+class _ModelFn(torch.autograd.Function):
+    """Whole-network autograd node: backward fills ``variables.grad`` and hands it to autograd as the
+    gradient of the flat parameter buffer."""
+
+    @staticmethod
+    def forward(ctx, point_cloud, flat, engine, train_enc, train_fc, decay, want_before):
+        recon, rot, trans, emb, before = engine.forward(point_cloud.contiguous(), train_enc, train_fc, decay,
+                                                        want_before)
+        ctx.engine = engine
+        ctx.mark_non_differentiable(*([before] if before is not None else []))
+        outs = (recon.clone(), rot.clone(), trans.clone(), emb.clone())
+        return outs + ((before,) if before is not None else (torch.empty(0, device=flat.device),))
+
+    @staticmethod
+    def backward(ctx, d_recon, d_rot, d_trans, d_emb, _d_before):
+        e = ctx.engine
+        z = lambda g, ref: torch.zeros_like(ref) if g is None else g  # noqa: E731
+        e.backward(z(d_recon, e.fc_y[e.branches[0][-1]]), z(d_rot, e.fc_y[e.branches[1][-1]]),
+                   z(d_trans, e.fc_y[e.branches[2][-1]]), d_emb)
+        return None, e.v.grad.clone(), None, None, None, None, None
+
+
+def _decay_tensor(engine: _Engine, bn_decay):
+    if bn_decay is None:
+        return None
+    if torch.is_tensor(bn_decay):
+        return bn_decay.to(device=engine.dev, dtype=torch.float32).reshape(1)
+    engine.decay_scalar.fill_(float(bn_decay))
+    return engine.decay_scalar
+
+
+def _check_cloud(point_cloud):
+    if point_cloud.dim() != 3:
+        raise _capi.InvalidArgumentError("point_cloud must be (batch_size, num_point, point_dim)")
+    if point_cloud.dtype != torch.float32:
+        raise _capi.InvalidArgumentError("point_cloud must be float32")
+    _capi.require_cuda(point_cloud, "get_model")
+
+
+def get_model_dgcnn_mean_6d(point_cloud, is_training_pl_encoder, is_training, k_neighbor, bn_decay=None,
+                            variables: Variables | None = None):
+    """DGCNN-style encoder (4 EdgeConv layers, kNN k=k_neighbor, mean aggregation, 320->1024 conv,
+    mean pool), FC decoder to 4N points and two 3-vector pose heads.
+
+    point_cloud f32[B,N,D] (xyz + class one-hot).  is_training_pl_encoder / is_training: batch-norm
+    mode of the encoder convs / of the FC layers (training: batch statistics + EMA update with
+    bn_decay, default 0.9; inference: EMA statistics).  Returns (net_recon [B,4N,3], net_rot [B,3],
+    net_trans [B,3], end_points{'layer_before_embedding' [B,N,1,1024], 'embedding' [B,1024]}).
+    """
+    _check_cloud(point_cloud)
+    b, n, d = point_cloud.shape
+    v = variables if variables is not None else get_variables("dgcnn", n, d, point_cloud.device)
+    eng = _engine_for(v, "dgcnn", b, n, d, int(k_neighbor))
+    recon, rot, trans, emb, before = _ModelFn.apply(point_cloud, v.flat, eng, bool(is_training_pl_encoder),
+                                                    bool(is_training), _decay_tensor(eng, bn_decay), True)
+    end_points = {"layer_before_embedding": before.view(b, n, 1, 1024), "embedding": emb,
+                  "nn_idx": [i.view(b, n, -1) for i in eng.idx]}
+    return recon.view(b, n * 4, 3), rot, trans, end_points
+
+
+def get_model_pn(point_cloud, is_training, bn_decay=None, variables: Variables | None = None):
+    """PointNet variant: per-point MLP 64-64-64-128-1024 (BN + ReLU), max pool over points, the same
+    FC decoder and pose heads.  Returns (net_recon, net_rot, net_trans, end_points{'embedding'})."""
+    _check_cloud(point_cloud)
+    b, n, d = point_cloud.shape
+    v = variables if variables is not None else get_variables("pn", n, d, point_cloud.device)
+    eng = _engine_for(v, "pn", b, n, d, 0)
+    recon, rot, trans, emb, _ = _ModelFn.apply(point_cloud, v.flat, eng, bool(is_training), bool(is_training),
+                                               _decay_tensor(eng, bn_decay), False)
+    return recon.view(b, n * 4, 3), rot, trans, {"embedding": emb}

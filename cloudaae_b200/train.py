@@ -1,0 +1,133 @@
+"""Training step of train_cloudAAE_ycbv.py (graph section :189-273) on one B200, data-parallel over N.
+
+``CloudAAETrainer.train_step`` runs, on the current CUDA stream and without host synchronisation
+(so the whole step can be captured in a CUDA graph):
+
+  step/bn_decay state -> input prep (noise, mean-normalise, one-hot) -> get_model_dgcnn_mean_6d
+  forward -> recon + mean -> chamfer nn_distance -> pose losses (rotation in float64) -> total loss
+  -> backward of everything -> [NCCL allreduce of the flat gradient] -> TF-style Adam.
+
+Data parallelism: one process per GPU, per-GPU batch fixed, batch-norm statistics
+stay per replica (the reference has a single replica and no sync-BN), ONE allreduce(sum) of the flat
+fp32 gradient buffer per step followed by a 1/world scale inside the Adam kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _capi
+from .models.pointnet_ycb_23_decoder_4 import NUM_CLASS, Variables, _Engine, dgcnn_layers, pn_layers
+
+
+class CloudAAETrainer:
+    def __init__(self, batch_size: int = 128, num_point: int = 256, k_neighbor: int = 10, learning_rate: float = 0.0008,
+                 model: str = "dgcnn", device="cuda", seed: int = 0, process_group=None,
+                 variables: Variables | None = None):
+        self.B, self.N, self.k = batch_size, num_point, k_neighbor
+        self.lr, self.beta1, self.beta2, self.eps = learning_rate, 0.9, 0.999, 1e-8
+        self.dev = torch.device(device)
+        self.D = 3 + NUM_CLASS
+        layers = dgcnn_layers(num_point, self.D) if model == "dgcnn" else pn_layers(num_point, self.D)
+        self.v = variables if variables is not None else Variables(layers, device=self.dev, seed=seed)
+        self.engine = _Engine(self.v, model, batch_size, num_point, self.D, k_neighbor if model == "dgcnn" else 0)
+        self.lib = _capi.lib()
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        B, M = batch_size, 4 * num_point
+        self.M = M
+        self.adam_m = torch.zeros_like(self.v.flat)
+        self.adam_v = torch.zeros_like(self.v.flat)
+        self.state = torch.zeros(4, dtype=torch.int32, device=self.dev)  # {step, adam_t, bn_decay(float bits)}
+        self.decay = self.state.view(torch.float32)[2:3]
+        self.x = torch.empty(B, num_point, self.D, **f32)
+        self.mean = torch.empty(B, 3, **f32)
+        self.recon = torch.empty(B, M, 3, **f32)
+        self.dist1 = torch.empty(B, M, **f32); self.dist2 = torch.empty(B, M, **f32)
+        self.idx1 = torch.empty(B, M, dtype=torch.int32, device=self.dev)
+        self.idx2 = torch.empty(B, M, dtype=torch.int32, device=self.dev)
+        self.gconst = torch.full((B, M), 1000.0 / (B * M), **f32)  # d(1000*mean(dist1+dist2))/d dist
+        self.d_recon = torch.empty(B, M, 3, **f32)
+        self.d_target = torch.empty(B, M, 3, **f32)
+        self.per_rot = torch.empty(B, dtype=torch.float64, device=self.dev)
+        self.per_trans = torch.empty(B, **f32)
+        self.d_rot = torch.empty(B, 3, **f32); self.d_trans = torch.empty(B, 3, **f32)
+        self.trans_pred = torch.empty(B, 3, **f32)
+        self.losses = torch.zeros(4, **f32)  # total, chamfer, trans, rot
+        self._graph = None
+        self._static = None
+
+    # ------------------------------------------------------------------
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _c(self, name, *args):
+        _capi.check(getattr(self.lib, name)(*args, self._st()), name)
+
+    def forward_losses(self, visible, target, class_id, translation, axisangle, noise):
+        """Forward pass + losses (+ the loss gradients w.r.t. the network outputs)."""
+        B, N, M = self.B, self.N, self.M
+        p = _Engine._p
+        assert visible.is_contiguous() and target.is_contiguous() and target.shape == (B, M, 3)
+        assert class_id.dtype == torch.int32
+        self._c("caae_prepare_input", B, N, visible.shape[1], p(visible), p(noise), p(class_id), NUM_CLASS, p(self.x),
+                p(self.mean))
+        recon, rot, trans, _, _ = self.engine.forward(self.x, True, True, self.decay)
+        self._c("caae_add_cloud_vec", B, M, p(recon), p(self.mean), p(self.recon))
+        self._c("caae_nn_distance", B, M, p(self.recon), M, p(target), p(self.dist1), p(self.idx1), p(self.dist2),
+                p(self.idx2))
+        self._c("caae_pose_losses", B, p(rot), p(axisangle), p(trans), p(self.mean), p(translation), 1.0 / B, 10.0 / B,
+                p(self.per_rot), p(self.per_trans), p(self.d_rot), p(self.d_trans), p(self.trans_pred))
+        self._c("caae_loss_reduce", B * M, p(self.dist1), p(self.dist2), B, p(self.per_trans), p(self.per_rot),
+                p(self.losses))
+        return self.losses
+
+    def backward(self, target):
+        B, M = self.B, self.M
+        p = _Engine._p
+        self._c("caae_nn_distance_grad", B, M, p(self.recon), M, p(target), p(self.gconst), p(self.idx1),
+                p(self.gconst), p(self.idx2), p(self.d_recon), p(self.d_target))
+        self.engine.backward(self.d_recon.view(B, 3 * M), self.d_rot, self.d_trans)
+
+    def apply_gradients(self):
+        p = _Engine._p
+        if self.world > 1:
+            torch.distributed.all_reduce(self.v.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        self._c("caae_adam_tf", self.v.flat.numel(), p(self.v.flat), p(self.v.grad), p(self.adam_m), p(self.adam_v),
+                p(self.state), self.lr, self.beta1, self.beta2, self.eps, 1.0 / self.world)
+
+    def train_step(self, visible, target, class_id, translation, axisangle, noise=None):
+        """One optimisation step.  visible f32[B,P>=N,3] (first N rows are the network input),
+        target f32[B,4N,3] (first 4N un-occluded visible points), class_id i32[B],
+        translation/axisangle f32[B,3] (labels), noise f32[B,N,3] or None.
+        Returns the device tensor [total, chamfer, trans, rot] (no host sync)."""
+        self._c("caae_step_begin", _Engine._p(self.state), self.B)
+        self.forward_losses(visible, target, class_id, translation, axisangle, noise)
+        self.backward(target)
+        self.apply_gradients()
+        return self.losses
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, visible, target, class_id, translation, axisangle, noise=None, warmup: int = 2):
+        """Capture train_step on static input buffers; afterwards `replay()` runs one step per call
+        on whatever those buffers hold.  Optimiser/BN state advances exactly as in eager mode."""
+        self._static = tuple(t.clone() if t is not None else None
+                             for t in (visible, target, class_id, translation, axisangle, noise))
+        snap = (self.v.flat.clone(), self.v.ema.clone(), self.adam_m.clone(), self.adam_v.clone(), self.state.clone())
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.train_step(*self._static)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.train_step(*self._static)
+        # warm-up and capture must not count as training steps
+        for dst, src in zip((self.v.flat, self.v.ema, self.adam_m, self.adam_v, self.state), snap):
+            dst.copy_(src)
+        return self._static
+
+    def replay(self):
+        self._graph.replay()
+        return self.losses

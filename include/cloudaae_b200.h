@@ -79,6 +79,81 @@ int caae_nn_distance_grad(int b, int n, const float* xyz1, int m, const float* x
                           const int* idx1, const float* grad_dist2, const int* idx2, float* grad_xyz1,
                           float* grad_xyz2, caae_stream_t stream);
 
+/* ==== model building blocks ====================================================================
+ * The reference builds its network from TensorFlow ops (cuBLAS/cuDNN kernels behind tf.matmul,
+ * tf.nn.conv2d, tf.nn.moments, tf.nn.top_k, tf.gather, ...; call sites utils/tf_util.py:161-173,
+ * 349-359, 492-510, 613-631, 655-665 and models/pointnet_ycb_23_decoder_4.py:327-455).  These entry
+ * points are what a binding of that layer stack calls instead.  Activations are row-major
+ * [rows, channels] fp32 with an explicit leading dimension so layers read/write slices of the
+ * 320-wide concat buffer in place.
+ */
+
+/* C[M,N] (+)= op(A)[M,K]*op(B)[K,N] (+ bias[N]); transX = 1 means the operand is stored transposed.
+ * fp32 FFMA arithmetic (tf.matmul / conv2d 1x1 and their gradients). */
+int caae_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                  float* C, int ldc, const float* bias, int accumulate, caae_stream_t stream);
+
+/* pairwise_xyz_distance + knn (tf_util.py:597-632): x [b*n, ldx] (first c channels), idx i32[b*n,k],
+ * k smallest of (|xi|^2 - 2 xi.xj) + |xj|^2, ascending, ties to the lower index, self included. */
+int caae_knn(int b, int n, int c, int k, const float* x, int ldx, int* idx, caae_stream_t stream);
+
+/* EdgeConv on the factorised projection PQ [b*n, >=2*cout] = [P | Q]: z_ij = P_i + Q_nn(i,j). */
+int caae_edge_parts(int b, int n); /* number of fp64 partial rows caae_edge_stats / _bwd_reduce write */
+int caae_edge_fold_weights(int c, int cout, const float* w, const float* bias, float* wf, float* bias_f, int ldw,
+                           caae_stream_t stream);
+int caae_edge_unfold_wgrad(int c, int cout, const float* dwf, int lddwf, float* dw, caae_stream_t stream);
+int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, double* parts,
+                    caae_stream_t stream);
+int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const float* scale,
+                    const float* shift, float* out, int ldo, caae_stream_t stream);
+int caae_edge_bwd_reduce(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
+                         const float* scale, const float* shift, const float* mean, const float* invstd,
+                         const float* dOut, int lddo, double* parts, caae_stream_t stream);
+int caae_edge_bwd_apply(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, const float* coef,
+                        const float* dOut, int lddo, float* dPQ, int lddpq, caae_stream_t stream);
+
+/* batch_norm_template (tf_util.py:473-511) on [R,C] activations: statistics, finalize (+EMA update),
+ * normalise+ReLU, pooled variants (mean over points: models/...:419; max: :59-60) and the backward. */
+int caae_col_parts(int R);
+int caae_col_stats(int R, int C, const float* Y, int ld, double* parts, caae_stream_t stream);
+int caae_bn_finalize(int C, const double* parts, int nparts, double count, const float* gamma, const float* beta,
+                     float* ema_mean, float* ema_var, const float* decay, float* scale, float* shift,
+                     float* save_mean, float* save_invstd, caae_stream_t stream);
+int caae_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* ema_mean, const float* ema_var,
+                        float* scale, float* shift, caae_stream_t stream);
+int caae_bn_bwd_finalize(int C, const double* parts, int nparts, double count, const float* gamma,
+                         const float* invstd, float* coef, float* dgamma, float* dbeta, caae_stream_t stream);
+int caae_bn_act(int R, int C, const float* Y, int ld, const float* scale, const float* shift, int relu, float* out,
+                int ldo, caae_stream_t stream);
+int caae_bn_act_pool(int groups, int group, int C, const float* Y, int ld, const float* scale, const float* shift,
+                     int maxpool, float* emb, int* argmax, caae_stream_t stream);
+int caae_bn_act_bwd_reduce(int R, int C, const float* Y, int ld, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, const float* dOut, int lddo, int group,
+                           float gscale, int relu, const int* argmax, double* parts, caae_stream_t stream);
+int caae_bn_act_bwd_apply(int R, int C, const float* Y, int ld, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, const float* coef, const float* dOut, int lddo,
+                          int group, float gscale, int relu, const int* argmax, float* dY, int lddy,
+                          caae_stream_t stream);
+int caae_colsum(int R, int C, const float* X, int ld, float* out, caae_stream_t stream);
+
+/* ==== losses, optimiser, step state ============================================================
+ * losses/angular_distance_taylor.py (float64), losses/trans_distance.py, losses/chamfer_loss.py,
+ * train_cloudAAE_ycbv.py:166-169,196-273 (bn_decay schedule, total loss, tf.train.AdamOptimizer). */
+int caae_pose_losses(int b, const float* rot_pred, const float* axag_label, const float* trans_res,
+                     const float* mean, const float* trans_label, float w_rot, float w_trans, double* per_rot,
+                     float* per_trans, float* d_rot, float* d_trans, float* trans_pred, caae_stream_t stream);
+int caae_loss_reduce(long npt, const float* dist1, const float* dist2, int b, const float* per_trans,
+                     const double* per_rot, float* losses, caae_stream_t stream);
+int caae_add_cloud_vec(int b, int npts, const float* in, const float* v, float* out, caae_stream_t stream);
+int caae_prepare_input(int b, int npoint, int vis_stride_pts, const float* visible, const float* noise,
+                       const int* class_id, int nclass, float* x, float* mean_out, caae_stream_t stream);
+/* state = {int step, int adam_t, float bn_decay} in device memory */
+int caae_step_begin(int* state, int batch_size, caae_stream_t stream);
+int caae_adam_tf(long n, float* p, const float* g, float* m, float* v, const int* state, float lr, float beta1,
+                 float beta2, float eps, float grad_scale, caae_stream_t stream);
+int caae_fill_f32(long n, float* p, float value, caae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,3 +60,40 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "caae_oracle" not in text and "libcloudaae_ref" not in text, f
+
+
+def _header_prototypes():
+    text = open(os.path.join(ROOT, "include", "cloudaae_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int|size_t|const char\*)\s+(caae_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        codes = ""
+        args = args.strip()
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a or a.startswith("caae_stream_t"):
+                    codes += "p"
+                elif a.startswith("int "):
+                    codes += "i"
+                elif a.startswith("long "):
+                    codes += "l"
+                elif a.startswith("float "):
+                    codes += "f"
+                elif a.startswith("double "):
+                    codes += "d"
+                else:
+                    raise AssertionError(f"unparsed argument {a!r} in {name}")
+        protos[name] = codes
+    return protos
+
+
+def test_ctypes_signatures_match_the_header():
+    import ctypes as C
+    from cloudaae_b200 import _capi
+    back = {C.c_int: "i", C.c_long: "l", C.c_float: "f", C.c_double: "d", C.c_void_p: "p"}
+    protos = _header_prototypes()
+    for name, argtypes in _capi._SIGNATURES.items():
+        got = "".join(back[a] for a in argtypes)
+        assert name in protos, name
+        assert got == protos[name], f"{name}: ctypes {got} vs header {protos[name]}"

@@ -1,0 +1,244 @@
+"""GPU parity of the network, losses, gradients and optimiser against the plain-PyTorch float64
+restatement of the reference graph (oracle/model_ref.py).  Tolerance: the north star's 1e-3 relative
+for features, poses, losses (fp32 here, so the observed errors are ~1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import model_ref as MR
+
+pytestmark = pytest.mark.gpu
+
+from cloudaae_b200 import _capi  # noqa: E402
+from cloudaae_b200.models import pointnet_ycb_23_decoder_4 as M  # noqa: E402
+from cloudaae_b200.train import CloudAAETrainer  # noqa: E402
+
+RTOL = 1e-3
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu() if torch.is_tensor(a) else torch.as_tensor(a).double()
+    b = b.detach().double().cpu() if torch.is_tensor(b) else torch.as_tensor(b).double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _gemm(ta, tb, Mm, N, K, A, lda, B, ldb, C, ldc, bias=None, acc=0):
+    lib = _capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    _capi.check(lib.caae_gemm_f32(ta, tb, Mm, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, C.data_ptr(), ldc,
+                                  None if bias is None else bias.data_ptr(), acc, st), "gemm")
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("Mm,N,K", [(128, 64, 16), (300, 130, 77), (1, 3, 1024), (64, 256, 4096), (33, 17, 5000)])
+def test_gemm_f32_all_layouts(ta, tb, Mm, N, K):
+    g = torch.Generator("cuda").manual_seed(Mm * 7 + N)
+    A = torch.randn((K, Mm) if ta else (Mm, K), device="cuda", generator=g)
+    B = torch.randn((N, K) if tb else (K, N), device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    C = torch.full((Mm, N + 3), 7.0, device="cuda")
+    _gemm(ta, tb, Mm, N, K, A, A.shape[1], B, B.shape[1], C, N + 3, bias)
+    want = (A.double().T if ta else A.double()) @ (B.double().T if tb else B.double()) + bias.double()
+    assert rel_err(C[:, :N], want) < 1e-5
+    assert (C[:, N:] == 7.0).all()  # leading-dimension padding untouched
+    C2 = C.clone()
+    _gemm(ta, tb, Mm, N, K, A, A.shape[1], B, B.shape[1], C2, N + 3, None, 1)
+    assert rel_err(C2[:, :N], want + want - bias.double()) < 1e-5
+
+
+def _knn(x, c, k):
+    b, n, ld = x.shape
+    idx = torch.empty(b, n, k, dtype=torch.int32, device="cuda")
+    _capi.check(_capi.lib().caae_knn(b, n, c, k, x.data_ptr(), ld, idx.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream), "knn")
+    return idx
+
+
+@pytest.mark.parametrize("b,n,c,ld,k", [(4, 256, 3, 24, 10), (3, 256, 64, 320, 10), (2, 100, 64, 64, 10),
+                                        (2, 600, 16, 16, 7), (1, 64, 128, 128, 20), (2, 10, 3, 3, 10)])
+def test_knn_matches_reference_topk(b, n, c, ld, k):
+    g = torch.Generator("cuda").manual_seed(n + c)
+    x = torch.randn(b, n, ld, device="cuda", generator=g)
+    idx = _knn(x, c, k).cpu().long()
+    xd = x[:, :, :c].double().cpu()
+    adj = MR.pairwise_xyz_distance(xd.unsqueeze(2) if c != 3 else xd)
+    want = MR.knn(adj, k)
+    same = (idx == want)
+    assert same.float().mean() > 0.995
+    # any disagreement must be a floating-point near-tie of the selected distances
+    dsel = torch.gather(adj, 2, idx)
+    dwant = torch.gather(adj, 2, want)
+    scale = adj.abs().max()
+    assert ((dsel - dwant).abs() <= 1e-5 * scale)[~same].all()
+    assert (idx[:, :, 0] == torch.arange(n)[None]).float().mean() > 0.99  # the point itself comes first
+    # ascending order of the (fp32) distances the kernel saw
+    assert (dsel[:, :, 1:] - dsel[:, :, :-1] >= -1e-5 * scale).all()
+
+
+def test_knn_exact_ties_pick_lower_index():
+    x = torch.zeros(1, 64, 3, device="cuda")
+    x[0, :, 0] = torch.arange(64, device="cuda").float() // 2  # pairs of identical points on a line
+    idx = _knn(x, 3, 4).cpu()
+    want = MR.knn(MR.pairwise_xyz_distance(x.double().cpu()), 4)
+    assert (idx == want).all()
+
+
+def _setup(model, b, n, seed=3):
+    layers = MR.DGCNN_LAYERS if model == "dgcnn" else MR.pn_layers(24, n)
+    if model == "dgcnn":
+        layers = list(layers)
+        layers[7] = ("dgcnn_output", 1024, n * 12, False)
+    p32 = MR.init_params(layers, seed=seed, perturb=True)
+    v = M.Variables(M.dgcnn_layers(n, 24) if model == "dgcnn" else M.pn_layers(n, 24), device="cuda", seed=None)
+    v.load_state_dict(p32)
+    p64 = {k: t.double().clone() for k, t in p32.items()}
+    rng = np.random.default_rng(seed)
+    clouds = cases.posed_ycb_clouds(1)[rng.integers(0, 21, b)]
+    cls = torch.from_numpy(rng.integers(0, 21, b).astype(np.int32))
+    visible = torch.from_numpy(np.ascontiguousarray(clouds[:, :n + 50])).float()
+    target = torch.from_numpy(np.ascontiguousarray(clouds[:, :4 * n])).float()
+    noise = torch.from_numpy((rng.standard_normal((b, n, 3)) * 0.004 / 3).astype(np.float32))
+    t, a, _ = cases.ycb_poses()
+    sel = rng.integers(0, len(t), b)
+    return v, p64, visible, target, cls, torch.from_numpy(t[sel]), torch.from_numpy(a[sel]), noise
+
+
+@pytest.mark.parametrize("model,b,n", [("dgcnn", 8, 256), ("dgcnn", 3, 128), ("pn", 8, 256), ("dgcnn", 1, 256)])
+def test_train_forward_losses_and_gradients(model, b, n):
+    v, p64, visible, target, cls, trans, axag, noise = _setup(model, b, n)
+    tr = CloudAAETrainer(batch_size=b, num_point=n, model=model, variables=v)
+    dev = lambda t: t.cuda().contiguous()  # noqa: E731
+    bn_decay = 0.9375
+    tr.decay.fill_(bn_decay)
+    losses = tr.forward_losses(dev(visible), dev(target), dev(cls), dev(trans), dev(axag), dev(noise))
+    tr.backward(dev(target))
+    torch.cuda.synchronize()
+
+    # ---- oracle (float64, literal TF graph); neighbour indices injected to take near-ties out
+    x64, mean64 = MR.prepare_input(visible.double(), cls, noise.double(), num_point=n)
+    assert rel_err(tr.x, x64) < 1e-5 and rel_err(tr.mean, mean64) < 1e-6
+    params = {k: t.clone().requires_grad_(not k.endswith(("ema_mean", "ema_var"))) for k, t in p64.items()}
+    ema = {}
+    override = [i.view(b, n, -1).cpu().long() for i in tr.engine.idx] if model == "dgcnn" else None
+    total, aux = MR.train_losses(params, x64, mean64, target.double(), trans.double(), axag.double(), bn_decay,
+                                 ema_updates=ema, nn_idx_override=override, model=model)
+    total.backward()
+
+    if model == "dgcnn":  # the kernel's own kNN agrees with the reference selection
+        _, _, _, ep = MR.get_model_dgcnn_mean_6d(x64, p64, True, True, 10, bn_decay)
+        agree = np.mean([(o == w).float().mean().item() for o, w in zip(override, ep["nn_idx"])])
+        assert agree > 0.995
+
+    assert rel_err(tr.engine.emb, aux["end_points"]["embedding"]) < RTOL
+    assert rel_err(tr.recon, aux["recon"]) < RTOL
+    assert rel_err(tr.engine.fc_y[tr.engine.branches[1][-1]], aux["rot_pred"]) < RTOL
+    assert rel_err(tr.trans_pred, aux["trans_pred"]) < RTOL
+    got = losses.cpu().double()
+    for i, key in enumerate(("chamfer", "trans", "rot"), start=1):
+        assert abs(got[i] - aux[key].item()) <= RTOL * abs(aux[key].item()), key
+    assert abs(got[0] - total.item()) <= RTOL * abs(total.item())
+
+    # ---- gradients of every trainable variable
+    worst = {}
+    for name in v.trainable_names():
+        g_ref = params[name].grad
+        g = v.grad_of(name)
+        if name.endswith("/biases") and (name.rsplit("/", 1)[0] + "/bn/gamma") in v:
+            # bias in front of a training-mode BN: mathematically zero gradient
+            assert g.abs().max().item() == 0.0
+            assert g_ref.abs().max().item() < 1e-6 * max(1.0, params[name.replace("biases", "weights")].grad.abs().max().item())
+            continue
+        worst[name] = rel_err(g, g_ref)
+    bad = {k: e for k, e in worst.items() if e > RTOL}
+    assert not bad, bad
+
+    # ---- EMA update  shadow = d*shadow + (1-d)*batch
+    for name, want in ema.items():
+        assert rel_err(v[name], want) < RTOL, name
+
+
+def test_adam_matches_tf_formula_and_step_state():
+    b, n = 4, 256
+    v, p64, visible, target, cls, trans, axag, noise = _setup("dgcnn", b, n)
+    tr = CloudAAETrainer(batch_size=b, num_point=n, variables=v)
+    dev = lambda t: t.cuda().contiguous()  # noqa: E731
+    args = (dev(visible), dev(target), dev(cls), dev(trans), dev(axag), dev(noise))
+    p0 = v.flat.clone()
+    m = torch.zeros_like(p0); vv = torch.zeros_like(p0)
+    want = p0.double().cpu()
+    m, vv = m.double().cpu(), vv.double().cpu()
+    for step in range(1, 4):
+        tr.train_step(*args)
+        g = v.grad.double().cpu()
+        want, m, vv = MR.adam_step(want, g, m, vv, step)
+        # bn_decay schedule: 0.5, then min(0.99, 1 - 0.5*0.5^floor(step*B/40))
+        assert tr.decay.item() == pytest.approx(MR.bn_decay_schedule(step - 1, b), rel=1e-6)
+        assert tr.state[0].item() == step
+        assert rel_err(v.flat, want) < 1e-5
+        want = v.flat.double().cpu()  # re-sync so errors do not compound through the next gradient
+        m, vv = tr.adam_m.double().cpu(), tr.adam_v.double().cpu()
+
+
+def test_eval_mode_uses_moving_averages_and_api_contract():
+    b, n = 2, 256
+    v, p64, visible, target, cls, trans, axag, noise = _setup("dgcnn", b, n, seed=5)
+    x64, _ = MR.prepare_input(visible.double(), cls, noise.double(), num_point=n)
+    x = x64.float().cuda()
+    recon, rot, tvec, ep = M.get_model_dgcnn_mean_6d(x, False, False, 10, variables=v)
+    assert recon.shape == (b, 4 * n, 3) and rot.shape == (b, 3) and tvec.shape == (b, 3)
+    assert ep["layer_before_embedding"].shape == (b, n, 1, 1024) and ep["embedding"].shape == (b, 1024)
+    override = [i.cpu().long() for i in ep["nn_idx"]]
+    r64, rot64, t64, ep64 = MR.get_model_dgcnn_mean_6d(x64, p64, False, False, 10, nn_idx_override=override)
+    assert rel_err(recon, r64) < RTOL and rel_err(rot, rot64) < RTOL and rel_err(tvec, t64) < RTOL
+    assert rel_err(ep["layer_before_embedding"], ep64["layer_before_embedding"]) < RTOL
+    assert rel_err(ep["embedding"], ep64["embedding"]) < RTOL
+    # mixed flags (encoder in training mode, FC in inference mode), bn_decay as a float
+    ema_before = v["dgcnn_fc1/bn/ema_mean"].clone()
+    enc_before = v["dgcnn1/bn/ema_mean"].clone()
+    M.get_model_dgcnn_mean_6d(x, True, False, 10, bn_decay=0.5, variables=v)
+    assert torch.equal(v["dgcnn_fc1/bn/ema_mean"], ema_before)
+    assert not torch.equal(v["dgcnn1/bn/ema_mean"], enc_before)
+    # PointNet variant
+    vp, pp64, *_ = _setup("pn", b, n, seed=6)
+    recon, rot, tvec, ep = M.get_model_pn(x, False, variables=vp)
+    r64, rot64, t64, ep64 = MR.get_model_pn(x64, pp64, False)
+    assert rel_err(recon, r64) < RTOL and rel_err(ep["embedding"], ep64["embedding"]) < RTOL
+
+
+def test_autograd_through_public_model_api():
+    b, n = 2, 256
+    v, p64, visible, target, cls, trans, axag, noise = _setup("dgcnn", b, n, seed=8)
+    x64, _ = MR.prepare_input(visible.double(), cls, noise.double(), num_point=n)
+    x = x64.float().cuda()
+    v.flat.requires_grad_(True)
+    recon, rot, tvec, ep = M.get_model_dgcnn_mean_6d(x, True, True, 10, bn_decay=0.9, variables=v)
+    loss = (recon ** 2).sum() + rot.sum() + (tvec * 2).sum()
+    loss.backward()
+    params = {k: t.clone().requires_grad_(not k.endswith(("ema_mean", "ema_var"))) for k, t in p64.items()}
+    override = [i.cpu().long() for i in ep["nn_idx"]]
+    r64, rot64, t64, _ = MR.get_model_dgcnn_mean_6d(x64, params, True, True, 10, 0.9, nn_idx_override=override)
+    ((r64 ** 2).sum() + rot64.sum() + (t64 * 2).sum()).backward()
+    flat_grad = v.flat.grad
+    for name in ("dgcnn1/weights", "dgcnn4/bn/gamma", "dgcnn_agg/weights", "dgcnn_output/biases", "dgcnn_rot_fc2/weights"):
+        o, shape = v.index[name]
+        g = flat_grad[o:o + int(np.prod(shape))].view(shape)
+        assert rel_err(g, params[name].grad) < RTOL, name
+
+
+def test_cuda_graph_replay_equals_eager():
+    b, n = 4, 256
+    v1, _, visible, target, cls, trans, axag, noise = _setup("dgcnn", b, n, seed=9)
+    v2, *_ = _setup("dgcnn", b, n, seed=9)
+    dev = lambda t: t.cuda().contiguous()  # noqa: E731
+    args = (dev(visible), dev(target), dev(cls), dev(trans), dev(axag), dev(noise))
+    eager = CloudAAETrainer(batch_size=b, num_point=n, variables=v1)
+    graph = CloudAAETrainer(batch_size=b, num_point=n, variables=v2)
+    graph.capture(*args)
+    for _ in range(3):
+        le = eager.train_step(*args).clone()
+        lg = graph.replay().clone()
+        torch.cuda.synchronize()
+        assert torch.allclose(le, lg, rtol=1e-4, atol=1e-6)
+    assert eager.state[0].item() == graph.state[0].item() == 3
+    assert rel_err(v2.flat, v1.flat) < 1e-3
