@@ -173,7 +173,7 @@ def get_model_dgcnn_mean_6d(point_cloud, params, is_training_pl_encoder, is_trai
     return net_recon, net_rot, net_trans, end_points
 
 
-def get_model_pn(point_cloud, params, is_training, bn_decay=None, ema_updates=None):
+def get_model_pn(point_cloud, params, is_training, bn_decay=None, ema_updates=None, argmax_override=None):
     """models/pointnet_ycb_23_decoder_4.py:23-89.  conv1 has kernel [1,point_dim] over the input
     expanded to [B,N,D,1], i.e. a per-point D->64 linear map; max-pool over the N points."""
     b, n, _ = point_cloud.shape
@@ -181,7 +181,12 @@ def get_model_pn(point_cloud, params, is_training, bn_decay=None, ema_updates=No
     net = point_cloud.unsqueeze(2)  # [B,N,1,D] — equivalent view of the [1,D] VALID convolution
     for scope in ("pn_conv1_encoder", "pn_conv2_encoder", "pn_conv3_encoder", "pn_conv4_encoder", "pn_conv5_encoder"):
         net = conv2d_1x1(net, params, scope, is_training, bn_decay, ema_updates)
-    net = net.max(dim=1, keepdim=True).values.reshape(b, -1)
+    pre_pool = net.reshape(b, n, -1)
+    if argmax_override is None:
+        net = pre_pool.max(dim=1).values
+    else:  # route through the given rows (takes max-pool near-ties out of a floating-point comparison)
+        net = torch.gather(pre_pool, 1, argmax_override.view(b, 1, -1)).reshape(b, -1)
+    end_points["pre_pool_max"] = pre_pool.max(dim=1).values
     end_points["embedding"] = net
     emb = net
     net = fully_connected(emb, params, "pn_fc1_decoder", is_training, bn_decay, ema_updates, bn=True)
@@ -256,14 +261,14 @@ def prepare_input(visible, class_id, noise, num_point=256, num_class=21):
 
 
 def train_losses(params, x, mean, target, translation, axisangle, bn_decay, k=10, ema_updates=None,
-                 nn_idx_override=None, model="dgcnn"):
+                 nn_idx_override=None, model="dgcnn", argmax_override=None):
     """train_cloudAAE_ycbv.py:228-268: model, chamfer on recon+mean, translation L2, rotation geodesic
     (float64), total = 1000*chamfer + 10*trans + rot."""
     if model == "dgcnn":
         recon, rot, trans_res, ep = get_model_dgcnn_mean_6d(x, params, True, True, k, bn_decay, ema_updates,
                                                             nn_idx_override)
     else:
-        recon, rot, trans_res, ep = get_model_pn(x, params, True, bn_decay, ema_updates)
+        recon, rot, trans_res, ep = get_model_pn(x, params, True, bn_decay, ema_updates, argmax_override)
     xyz_recon = recon + mean.unsqueeze(1)
     trans_pred = trans_res + mean
     xyz_loss, _ = chamfer_get_loss(xyz_recon, target)
