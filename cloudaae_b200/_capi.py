@@ -41,6 +41,7 @@ _SIGNATURES = {
     "caae_nn_distance_grad": "iipippppppp" "p",
     # model building blocks
     "caae_gemm_f32": "iiiiipipipipi" "p",
+    "caae_gemm_tf32": "iiiiipipipipi" "p",
     "caae_knn": "iiiipip" "p",
     "caae_edge_stats": "iiiipipp" "p",
     "caae_edge_apply": "iiiipippppi" "p",
@@ -73,6 +74,7 @@ _SPECIAL = {
     "caae_fps_scratch_bytes": ([_int, _int], ctypes.c_size_t),
     "caae_edge_parts": ([_int, _int], _int),
     "caae_col_parts": ([_int], _int),
+    "caae_gemm_tf32_supported": ([_int, _int, _int, _int, _int, _ptr, _int, _ptr, _int], _int),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(list(_SIGNATURES) + list(_SPECIAL)))

@@ -115,9 +115,9 @@ extern "C" int caae_gemm_f32(int transa, int transb, int M, int N, int K, const 
   cudaStream_t s = as_stream(stream);
   const int tiles = ((M + GBM - 1) / GBM) * ((N + GBN - 1) / GBN);
   int splits = 1;
-  if (tiles < kNumSMs && K >= 1024) {
+  if (tiles < kNumSMs && K >= 256) {
     splits = (2 * kNumSMs + tiles - 1) / tiles;
-    const int max_splits = K / 256;
+    const int max_splits = K / 64;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }

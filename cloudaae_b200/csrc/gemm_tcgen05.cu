@@ -1,0 +1,348 @@
+// gemm_tcgen05.cu — TF32 tensor-core GEMM for sm_100a: tcgen05.mma with the accumulator in TMEM,
+// operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier pipeline.
+//
+//   C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N]),  fp32 in / fp32 out, TF32 multiply, fp32 accumulate.
+//
+// This is the only dense contraction of the model that matters for time: conv2d 320->1024
+// `dgcnn_agg` (reference models/pointnet_ycb_23_decoder_4.py:410-413 via utils/tf_util.py:161) with
+// M = B*N = 32768 rows — forward, data gradient and weight gradient are 64 GFLOP of the ~70 GFLOP
+// step — plus the FC stack and the EdgeConv projections.  All four operand layouts are native:
+// an operand stored with K contiguous is consumed as a K-major UMMA operand, one stored with M/N
+// contiguous as an MN-major operand (instruction-descriptor major bits + a different TMA box), so
+// neither the weight gradient X^T dY (both operands MN-major) nor the data gradient dY W^T needs a
+// transposed copy in HBM.
+//
+// CTA = one 128 x 128 output tile (x one K split).  192 threads, warp-specialised:
+//   warp 0      TMA producer (one elected lane): per 32-wide K block, 16 KB of A and 16 KB of B
+//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma 128x128x8 per K block
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (each warp its own TMEM lane quadrant) -> bias /
+//               accumulate / split-K reduction -> global stores of whole 128-byte lines
+// 3 stages x 32 KB of shared memory and 128 TMEM columns per CTA, so two CTAs are co-resident per
+// SM and one CTA's epilogue overlaps the other's main loop.
+//
+// Shared-memory operand layouts (fp32 elements, T = 4 elements per 16 bytes):
+//   K-major  (SWIZZLE_128B): row r (an M or N index) at r*128 B holds 32 consecutive K elements;
+//            8-row groups every 1024 B (SBO = 1024).  One TMA box {32 (K), 128 (rows)} per stage.
+//            A K-step of 8 elements advances the descriptor start address by 32 B.
+//   MN-major (SWIZZLE_128B): K-row r at r*128 B holds 32 consecutive M/N elements; 8-row groups
+//            every 1024 B (SBO); the next 32 M/N elements start LBO = 4096 B later.  Four TMA boxes
+//            {32 (M/N), 32 (K rows)} per stage.  A K-step of 8 rows advances the start by 1024 B.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace caae {
+
+constexpr int TBM = 128, TBN = 128, TBK = 32;  // CTA tile; TBK fp32 = one 128-byte swizzle row
+constexpr int TSTAGES = 3;
+constexpr int TTHREADS = 192;
+constexpr uint32_t TSTAGE_A = TBM * TBK * 4, TSTAGE_B = TBN * TBK * 4;  // 16 KB each
+constexpr uint32_t TSMEM_BYTES = TSTAGES * (TSTAGE_A + TSTAGE_B) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 128;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct GemmParams {
+  int M, N, K;
+  float* C;
+  int ldc;
+  const float* bias;
+  int accumulate;   // C += (splits == 1)
+  int kb_per_split; // K blocks per blockIdx.z
+  int atomic;       // split-K: reduce with red.global.add
+  int a_mn, b_mn;   // operand majors (0 = K-major, 1 = MN-major)
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(TTHREADS)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-byte alignment
+  const uint32_t smem_a = base, smem_b = base + TSTAGES * TSTAGE_A;
+  const uint32_t bars = smem_b + TSTAGES * TSTAGE_B;
+  const uint32_t full0 = bars, empty0 = bars + 8 * TSTAGES, tmem_full = bars + 16 * TSTAGES;
+  const uint32_t tmem_slot = bars + 16 * TSTAGES + 8;
+  // generic pointer to the TMEM-address slot
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+  const int num_kb_total = (p.K + TBK - 1) / TBK;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+  const int num_kb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % TSTAGES;
+        const uint32_t ph = (i / TSTAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, TSTAGE_A + TSTAGE_B);
+        const int k0 = (kb0 + i) * TBK;
+        const uint32_t da = smem_a + s * TSTAGE_A, db = smem_b + s * TSTAGE_B;
+        if (p.a_mn) {
+#pragma unroll
+          for (int c = 0; c < TBM / 32; ++c) tma_load_2d(da + c * 4096, &map_a, full0 + 8 * s, m0 + 32 * c, k0);
+        } else {
+          tma_load_2d(da, &map_a, full0 + 8 * s, k0, m0);
+        }
+        if (p.b_mn) {
+#pragma unroll
+          for (int c = 0; c < TBN / 32; ++c) tma_load_2d(db + c * 4096, &map_b, full0 + 8 * s, n0 + 32 * c, k0);
+        } else {
+          tma_load_2d(db, &map_b, full0 + 8 * s, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % TSTAGES;
+        const uint32_t ph = (i / TSTAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t da = smem_a + s * TSTAGE_A, db = smem_b + s * TSTAGE_B;
+#pragma unroll
+        for (int k = 0; k < TBK / 8; ++k) {
+          const uint64_t adesc = make_smem_desc(da + k * a_kstep, a_lbo, 1024u);
+          const uint64_t bdesc = make_smem_desc(db + k * b_kstep, b_lbo, 1024u);
+          umma_tf32(tmem_base, adesc, bdesc, p.idesc, (uint32_t)((i | k) != 0));
+        }
+        umma_commit(empty0 + 8 * s);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: warps 2..5 -> TMEM lane quadrants 2,3,0,1 =====
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < TBN; c0 += 32) {
+      uint32_t r[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row < p.M) {
+        float* crow = p.C + (size_t)row * p.ldc + n0 + c0;
+        const int ncols = min(32, p.N - (n0 + c0));
+        if (ncols == 32 && !p.atomic && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+            if (add_bias) {
+              const float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + j);
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            }
+            if (p.accumulate) {
+              const float4 o = *reinterpret_cast<const float4*>(crow + j);
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *reinterpret_cast<float4*>(crow + j) = v;
+          }
+        } else {
+          for (int j = 0; j < ncols; ++j) {
+            float v = __uint_as_float(r[j]) + (add_bias ? p.bias[n0 + c0 + j] : 0.f);
+            if (p.atomic) atomicAdd(crow + j, v);
+            else crow[j] = p.accumulate ? crow[j] + v : v;
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+__global__ void zero_matrix2_kernel(int M, int N, float* __restrict__ C, int ldc) {
+  const long total = (long)M * N;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
+    C[(e / N) * ldc + (e % N)] = 0.f;
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor with `inner` contiguous elements per row, `outer` rows, row pitch ld elements
+static int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return CAAE_E_UNSUPPORTED;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : CAAE_E_UNSUPPORTED;
+}
+
+}  // namespace caae
+
+using namespace caae;
+
+// 1 when the TF32 tensor-core kernel accepts this problem (TMA alignment rules), else 0.
+extern "C" int caae_gemm_tf32_supported(int transa, int transb, int M, int N, int K, const float* A, int lda,
+                                        const float* B, int ldb) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return 0;
+  if ((lda & 3) || (ldb & 3)) return 0;
+  (void)transa; (void)transb;
+  return 1;
+}
+
+extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
+                              int ldb, float* C, int ldc, const float* bias, int accumulate, caae_stream_t stream) {
+  CAAE_RETURN_IF(M < 0 || N < 0 || K < 0, CAAE_E_BADSHAPE);
+  if (M == 0 || N == 0) return CAAE_OK;
+  CAAE_RETURN_IF(!C || !A || !B, CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(ldc < N || lda < (transa ? M : K) || ldb < (transb ? K : N), CAAE_E_BADSHAPE);
+  CAAE_RETURN_IF(!caae_gemm_tf32_supported(transa, transb, M, N, K, A, lda, B, ldb), CAAE_E_UNSUPPORTED);
+  cudaStream_t s = as_stream(stream);
+
+  CUtensorMap map_a, map_b;
+  int rc;
+  // A: transa = 0 -> stored [M,K] (K contiguous, K-major); transa = 1 -> stored [K,M] (M contiguous, MN-major)
+  rc = transa ? make_map(&map_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK)
+              : make_map(&map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM);
+  if (rc) return rc;
+  // B: transb = 1 -> stored [N,K] (K-major); transb = 0 -> stored [K,N] (N contiguous, MN-major)
+  rc = transb ? make_map(&map_b, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, TBN)
+              : make_map(&map_b, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
+  p.a_mn = transa ? 1 : 0;
+  p.b_mn = transb ? 0 : 1;
+  // instruction descriptor: c_format F32 (bit 4), a/b format TF32 (=2) at bits 7 / 10, majors at 15 / 16,
+  // N>>3 at bit 17, M>>4 at bit 24
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+            ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+  const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
+  const int num_kb = (K + TBK - 1) / TBK;
+  int splits = 1;
+  const int tiles = tiles_m * tiles_n;
+  if (tiles < kNumSMs && num_kb >= 8) {
+    splits = (2 * kNumSMs + tiles - 1) / tiles;
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.atomic = splits > 1;
+  p.accumulate = p.atomic ? 0 : accumulate;
+  if (p.atomic && !accumulate) {
+    const long total = (long)M * N;
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    zero_matrix2_kernel<<<blocks, 256, 0, s>>>(M, N, C, ldc);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid(tiles_n, tiles_m, splits);
+  CAAE_RETURN_IF(grid.y > 65535 || grid.z > 65535, CAAE_E_BADSHAPE);
+  gemm_tf32_kernel<<<grid, TTHREADS, TSMEM_BYTES, s>>>(map_a, map_b, p);
+  return CAAE_LAUNCH_STATUS();
+}

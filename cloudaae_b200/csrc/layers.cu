@@ -188,17 +188,35 @@ col_reduce_kernel(int R, int C, const float* __restrict__ Y, int ld, const float
   }
 }
 
-// forward finalize: one thread per channel
-__global__ void bn_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ ema_mean, float* __restrict__ ema_var,
-                                   const float* __restrict__ decay, float* __restrict__ scale,
-                                   float* __restrict__ shift, float* __restrict__ save_mean,
-                                   float* __restrict__ save_invstd) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int p = 0; p < nparts; ++p) { s += parts[(size_t)p * 2 * C + ch]; ss += parts[(size_t)p * 2 * C + C + ch]; }
+// Fixed-order reduction of the fp64 partials: block (32, 8) = 32 channels x 8 partial lanes.
+__device__ __forceinline__ void reduce_parts(int C, const double* __restrict__ parts, int nparts, int ch,
+                                             double& s, double& ss) {
+  __shared__ double r_a[8][32], r_b[8][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  double a = 0.0, b = 0.0;
+  if (ch < C)
+    for (int p = ty; p < nparts; p += 8) { a += parts[(size_t)p * 2 * C + ch]; b += parts[(size_t)p * 2 * C + C + ch]; }
+  r_a[ty][tx] = a; r_b[ty][tx] = b;
+  __syncthreads();
+  s = 0.0; ss = 0.0;
+  if (ty == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { s += r_a[r][tx]; ss += r_b[r][tx]; }
+  }
+}
+
+// forward finalize
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ ema_mean, float* __restrict__ ema_var,
+                   const float* __restrict__ decay, float* __restrict__ scale,
+                   float* __restrict__ shift, float* __restrict__ save_mean,
+                   float* __restrict__ save_invstd) {
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  double s, ss;
+  reduce_parts(C, parts, nparts, ch, s, ss);
+  if (threadIdx.y != 0 || ch >= C) return;
   const double m = s / count;
   double v = ss / count - m * m;  // biased variance, as tf.nn.moments
   if (v < 0.0) v = 0.0;
@@ -228,14 +246,14 @@ __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, co
 }
 
 // backward finalize: coef = [mean(dy) | mean(dy*yhat) | gamma*invstd]; dgamma = sum dy*yhat, dbeta = sum dy
-__global__ void bn_bwd_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double count,
-                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
-                                       float* __restrict__ coef, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int p = 0; p < nparts; ++p) { s += parts[(size_t)p * 2 * C + ch]; ss += parts[(size_t)p * 2 * C + C + ch]; }
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double count,
+                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  double s, ss;
+  reduce_parts(C, parts, nparts, ch, s, ss);
+  if (threadIdx.y != 0 || ch >= C) return;
   coef[ch] = (float)(s / count);
   coef[C + ch] = (float)(ss / count);
   coef[2 * C + ch] = gamma[ch] * invstd[ch];
@@ -430,7 +448,7 @@ extern "C" int caae_bn_finalize(int C, const double* parts, int nparts, double c
                                 caae_stream_t stream) {
   CAAE_RETURN_IF(C <= 0 || nparts <= 0 || count <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!parts || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd, CAAE_E_NULLPTR);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, beta, ema_mean,
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, beta, ema_mean,
                                                                      ema_var, decay, scale, shift, save_mean,
                                                                      save_invstd);
   return CAAE_LAUNCH_STATUS();
@@ -449,7 +467,7 @@ extern "C" int caae_bn_bwd_finalize(int C, const double* parts, int nparts, doub
                                     caae_stream_t stream) {
   CAAE_RETURN_IF(C <= 0 || nparts <= 0 || count <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!parts || !gamma || !invstd || !coef || !dgamma || !dbeta, CAAE_E_NULLPTR);
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, invstd, coef,
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, invstd, coef,
                                                                          dgamma, dbeta);
   return CAAE_LAUNCH_STATUS();
 }

@@ -93,6 +93,14 @@ int caae_nn_distance_grad(int b, int n, const float* xyz1, int m, const float* x
 int caae_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                   float* C, int ldc, const float* bias, int accumulate, caae_stream_t stream);
 
+/* Same contract on the 5th-generation tensor cores: TF32 multiply, fp32 accumulate in TMEM, operands via
+ * TMA (tcgen05.mma; no transposed copies for any layout).  Requires 16-byte aligned A/B and lda, ldb
+ * multiples of 4; caae_gemm_tf32_supported() returns 1 when the problem qualifies. */
+int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                   float* C, int ldc, const float* bias, int accumulate, caae_stream_t stream);
+int caae_gemm_tf32_supported(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
+                             int ldb);
+
 /* pairwise_xyz_distance + knn (tf_util.py:597-632): x [b*n, ldx] (first c channels), idx i32[b*n,k],
  * k smallest of (|xi|^2 - 2 xi.xj) + |xj|^2, ascending, ties to the lower index, self included. */
 int caae_knn(int b, int n, int c, int k, const float* x, int ldx, int* idx, caae_stream_t stream);

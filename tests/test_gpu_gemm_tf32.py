@@ -1,0 +1,67 @@
+"""tcgen05 TF32 GEMM vs float64 matmul: every operand layout, tails, split-K, bias / accumulate."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cloudaae_b200 import _capi  # noqa: E402
+
+
+def _run(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, acc=0):
+    lib = _capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.caae_gemm_tf32_supported(ta, tb, M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb) == 1
+    _capi.check(lib.caae_gemm_tf32(ta, tb, M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, C.data_ptr(), ldc,
+                                   None if bias is None else bias.data_ptr(), acc, st), "caae_gemm_tf32")
+
+
+def _pad4(x):
+    return (x + 3) // 4 * 4
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 96), (300, 130, 77), (4096, 1024, 320), (128, 3072, 1024),
+                                   (320, 1024, 8192), (64, 64, 4096), (1, 8, 8)])
+def test_gemm_tf32_layouts(ta, tb, M, N, K):
+    g = torch.Generator("cuda").manual_seed(M + 3 * N + 7 * K + ta + 2 * tb)
+    a_shape = (K, _pad4(M)) if ta else (M, _pad4(K))
+    b_shape = (N, _pad4(K)) if tb else (K, _pad4(N))
+    A = torch.randn(a_shape, device="cuda", generator=g)
+    B = torch.randn(b_shape, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ldc = N + 5
+    C = torch.full((M, ldc), 3.0, device="cuda")
+    _run(ta, tb, M, N, K, A, A.shape[1], B, B.shape[1], C, ldc, bias)
+    torch.cuda.synchronize()
+    Ad = (A[:, :M].double().T if ta else A[:, :K].double())
+    Bd = (B[:, :K].double().T if tb else B[:, :N].double())
+    want = Ad @ Bd + bias.double()
+    scale = (Ad.abs() @ Bd.abs()).max()  # TF32 rounds each factor to 11 bits: error ~ 2^-11 * sum|a||b| / sqrt(K)
+    err = (C[:, :N].double() - want).abs().max()
+    assert err <= 2e-3 * scale / max(K, 1) ** 0.5 + 1e-6, (err.item(), scale.item())
+    assert (C[:, N:] == 3.0).all()
+    # accumulate on top
+    C2 = C.clone()
+    _run(ta, tb, M, N, K, A, A.shape[1], B, B.shape[1], C2, ldc, None, 1)
+    torch.cuda.synchronize()
+    err2 = (C2[:, :N].double() - (2 * want - bias.double())).abs().max()
+    assert err2 <= 4e-3 * scale / max(K, 1) ** 0.5 + 1e-6
+
+
+def test_gemm_tf32_rejects_misaligned():
+    lib = _capi.lib()
+    A = torch.zeros(16, 6, device="cuda")
+    assert lib.caae_gemm_tf32_supported(0, 0, 16, 8, 6, A.data_ptr(), 6, A.data_ptr(), 8) == 0
+    assert lib.caae_gemm_tf32(0, 0, 16, 8, 6, A.data_ptr(), 6, A.data_ptr(), 8, A.data_ptr(), 8, None, 0, None) == -4
+
+
+def test_gemm_tf32_reads_column_slices_in_place():
+    """Operands are slices of the 320-wide concat buffer (ld = 320), as the model uses them."""
+    g = torch.Generator("cuda").manual_seed(5)
+    H = torch.randn(2048, 320, device="cuda", generator=g)
+    W = torch.randn(64, 256, device="cuda", generator=g)
+    C = torch.empty(2048, 256, device="cuda")
+    X = H[:, 64:128]
+    _run(0, 0, 2048, 256, 64, X, 320, W, 256, C, 256)
+    want = X.double() @ W.double()
+    assert (C.double() - want).abs().max() <= 2e-3 * (X.abs().double() @ W.abs().double()).max() / 8
