@@ -24,9 +24,11 @@
 //   K-major  (SWIZZLE_128B): row r (an M or N index) at r*128 B holds 32 consecutive K elements;
 //            8-row groups every 1024 B (SBO = 1024).  One TMA box {32 (K), 128 (rows)} per stage.
 //            A K-step of 8 elements advances the descriptor start address by 32 B.
-//   MN-major (SWIZZLE_128B): K-row r at r*128 B holds 32 consecutive M/N elements; 8-row groups
-//            every 1024 B (SBO); the next 32 M/N elements start LBO = 4096 B later.  Four TMA boxes
-//            {32 (M/N), 32 (K rows)} per stage.  A K-step of 8 rows advances the start by 1024 B.
+//   MN-major (SWIZZLE_128B with 32-byte atoms — the only MN-major layout tcgen05 accepts for 32-bit
+//            operands; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, descriptor layout type 1):
+//            K-row r at r*128 B holds 32 consecutive M/N elements; 4-row groups every 512 B (SBO);
+//            the next 32 M/N elements start LBO = 4096 B later.  Four TMA boxes {32 (M/N), 32 (K rows)}
+//            per stage.  A K-step of 8 rows advances the start address by 1024 B.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -87,10 +89,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"):
-//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 |
+//   [61,64) layout type (2 = SWIZZLE_128B, 1 = SWIZZLE_128B with 32-byte atoms)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 
 struct GemmParams {
@@ -167,6 +171,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
       const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
+      const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
+      const uint32_t a_lt = p.a_mn ? 1u : 2u, b_lt = p.b_mn ? 1u : 2u;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % TSTAGES;
         const uint32_t ph = (i / TSTAGES) & 1;
@@ -175,8 +181,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t da = smem_a + s * TSTAGE_A, db = smem_b + s * TSTAGE_B;
 #pragma unroll
         for (int k = 0; k < TBK / 8; ++k) {
-          const uint64_t adesc = make_smem_desc(da + k * a_kstep, a_lbo, 1024u);
-          const uint64_t bdesc = make_smem_desc(db + k * b_kstep, b_lbo, 1024u);
+          const uint64_t adesc = make_smem_desc(da + k * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t bdesc = make_smem_desc(db + k * b_kstep, b_lbo, b_sbo, b_lt);
           umma_tf32(tmem_base, adesc, bdesc, p.idesc, (uint32_t)((i | k) != 0));
         }
         umma_commit(empty0 + 8 * s);  // frees the stage once these MMAs have read it
@@ -262,15 +268,17 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor with `inner` contiguous elements per row, `outer` rows, row pitch ld elements
 static int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                    uint32_t box_outer) {
+                    uint32_t box_outer, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return CAAE_E_UNSUPPORTED;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * sizeof(float)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : CAAE_E_UNSUPPORTED;
 }
@@ -301,12 +309,12 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
   CUtensorMap map_a, map_b;
   int rc;
   // A: transa = 0 -> stored [M,K] (K contiguous, K-major); transa = 1 -> stored [K,M] (M contiguous, MN-major)
-  rc = transa ? make_map(&map_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK)
-              : make_map(&map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM);
+  rc = transa ? make_map(&map_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK, true)
+              : make_map(&map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
   if (rc) return rc;
   // B: transb = 1 -> stored [N,K] (K-major); transb = 0 -> stored [K,N] (N contiguous, MN-major)
-  rc = transb ? make_map(&map_b, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, TBN)
-              : make_map(&map_b, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK);
+  rc = transb ? make_map(&map_b, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, TBN, false)
+              : make_map(&map_b, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
   if (rc) return rc;
 
   GemmParams p;

@@ -13,6 +13,7 @@ in ONE flat fp32 buffer — the operand of the fused Adam kernel and of the data
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -142,7 +143,10 @@ class _Engine:
     from the slice layer l-1 wrote.
     """
 
-    def __init__(self, variables: Variables, model: str, batch: int, num_point: int, point_dim: int, k: int = 10):
+    def __init__(self, variables: Variables, model: str, batch: int, num_point: int, point_dim: int, k: int = 10,
+                 precision: str | None = None):
+        self.precision = precision or os.environ.get("CLOUDAAE_GEMM", "tf32")
+        assert self.precision in ("tf32", "fp32")
         self.v = variables
         self.model = model
         self.B, self.N, self.D, self.k = batch, num_point, point_dim, k
@@ -212,7 +216,17 @@ class _Engine:
         return None if t is None else t.data_ptr()
 
     def _gemm(self, ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, acc=0):
-        self._c("caae_gemm_f32", ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), acc)
+        """Dense contraction.  precision 'tf32': the tcgen05 tensor-core kernel (TF32 multiply, fp32
+        accumulate) for the LARGE contractions — in practice the three dgcnn_agg / pn_conv5 GEMMs
+        (forward, data gradient, weight gradient: >90 % of the step's FLOPs).  Everything else, and
+        everything with precision 'fp32', runs on the FFMA kernel: the FC stack (M = batch) is
+        weight-bandwidth bound, and its batch-norm backward over only `batch` rows amplifies TF32
+        rounding of the pre-activations far beyond the 1e-3 parity budget."""
+        fn = "caae_gemm_f32"
+        if (self.precision == "tf32" and M * N * K >= (1 << 29) and
+                self.lib.caae_gemm_tf32_supported(ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb)):
+            fn = "caae_gemm_tf32"
+        self._c(fn, ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), acc)
 
     def _bn_coeffs(self, scope, training, nparts, count, decay):
         v, bn = self.v, self.bn[scope]
@@ -405,7 +419,7 @@ def reset_default_variables():
 
 
 def _engine_for(variables: Variables, model: str, b: int, n: int, d: int, k: int) -> _Engine:
-    key = (id(variables), model, b, n, d, k)
+    key = (id(variables), model, b, n, d, k, os.environ.get("CLOUDAAE_GEMM", "tf32"))
     if key not in _ENGINES:
         _ENGINES[key] = _Engine(variables, model, b, n, d, k)
     return _ENGINES[key]

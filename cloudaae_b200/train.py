@@ -22,14 +22,15 @@ from .models.pointnet_ycb_23_decoder_4 import NUM_CLASS, Variables, _Engine, dgc
 class CloudAAETrainer:
     def __init__(self, batch_size: int = 128, num_point: int = 256, k_neighbor: int = 10, learning_rate: float = 0.0008,
                  model: str = "dgcnn", device="cuda", seed: int = 0, process_group=None,
-                 variables: Variables | None = None):
+                 variables: Variables | None = None, precision: str | None = None):
         self.B, self.N, self.k = batch_size, num_point, k_neighbor
         self.lr, self.beta1, self.beta2, self.eps = learning_rate, 0.9, 0.999, 1e-8
         self.dev = torch.device(device)
         self.D = 3 + NUM_CLASS
         layers = dgcnn_layers(num_point, self.D) if model == "dgcnn" else pn_layers(num_point, self.D)
         self.v = variables if variables is not None else Variables(layers, device=self.dev, seed=seed)
-        self.engine = _Engine(self.v, model, batch_size, num_point, self.D, k_neighbor if model == "dgcnn" else 0)
+        self.engine = _Engine(self.v, model, batch_size, num_point, self.D, k_neighbor if model == "dgcnn" else 0,
+                              precision=precision)
         self.lib = _capi.lib()
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)

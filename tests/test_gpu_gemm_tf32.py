@@ -38,14 +38,14 @@ def test_gemm_tf32_layouts(ta, tb, M, N, K):
     want = Ad @ Bd + bias.double()
     scale = (Ad.abs() @ Bd.abs()).max()  # TF32 rounds each factor to 11 bits: error ~ 2^-11 * sum|a||b| / sqrt(K)
     err = (C[:, :N].double() - want).abs().max()
-    assert err <= 2e-3 * scale / max(K, 1) ** 0.5 + 1e-6, (err.item(), scale.item())
+    assert err <= 4e-3 * scale / max(K, 1) ** 0.5 + 1e-6, (err.item(), scale.item())
     assert (C[:, N:] == 3.0).all()
     # accumulate on top
     C2 = C.clone()
     _run(ta, tb, M, N, K, A, A.shape[1], B, B.shape[1], C2, ldc, None, 1)
     torch.cuda.synchronize()
     err2 = (C2[:, :N].double() - (2 * want - bias.double())).abs().max()
-    assert err2 <= 4e-3 * scale / max(K, 1) ** 0.5 + 1e-6
+    assert err2 <= 8e-3 * scale / max(K, 1) ** 0.5 + 1e-6
 
 
 def test_gemm_tf32_rejects_misaligned():

@@ -113,10 +113,11 @@ def _setup(model, b, n, seed=3):
     return v, p64, visible, target, cls, torch.from_numpy(t[sel]), torch.from_numpy(a[sel]), noise
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
 @pytest.mark.parametrize("model,b,n", [("dgcnn", 8, 256), ("dgcnn", 3, 128), ("pn", 8, 256), ("dgcnn", 1, 256)])
-def test_train_forward_losses_and_gradients(model, b, n):
+def test_train_forward_losses_and_gradients(model, b, n, precision):
     v, p64, visible, target, cls, trans, axag, noise = _setup(model, b, n)
-    tr = CloudAAETrainer(batch_size=b, num_point=n, model=model, variables=v)
+    tr = CloudAAETrainer(batch_size=b, num_point=n, model=model, variables=v, precision=precision)
     dev = lambda t: t.cuda().contiguous()  # noqa: E731
     bn_decay = 0.9375
     tr.decay.fill_(bn_decay)
@@ -174,7 +175,7 @@ def test_train_forward_losses_and_gradients(model, b, n):
 def test_adam_matches_tf_formula_and_step_state():
     b, n = 4, 256
     v, p64, visible, target, cls, trans, axag, noise = _setup("dgcnn", b, n)
-    tr = CloudAAETrainer(batch_size=b, num_point=n, variables=v)
+    tr = CloudAAETrainer(batch_size=b, num_point=n, variables=v, precision="fp32")
     dev = lambda t: t.cuda().contiguous()  # noqa: E731
     args = (dev(visible), dev(target), dev(cls), dev(trans), dev(axag), dev(noise))
     p0 = v.flat.clone()
