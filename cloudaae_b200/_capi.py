@@ -72,7 +72,7 @@ _SPECIAL = {
     "caae_abi_version": ([], _int),
     "caae_status_string": ([_int], ctypes.c_char_p),
     "caae_fps_scratch_bytes": ([_int, _int], ctypes.c_size_t),
-    "caae_edge_parts": ([_int, _int], _int),
+    "caae_edge_parts": ([_int, _int, _int, _int, _int], _int),
     "caae_col_parts": ([_int], _int),
     "caae_gemm_tf32_supported": ([_int, _int, _int, _int, _int, _ptr, _int, _ptr, _int], _int),
 }

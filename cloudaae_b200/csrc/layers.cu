@@ -188,25 +188,36 @@ col_reduce_kernel(int R, int C, const float* __restrict__ Y, int ld, const float
   }
 }
 
-// Fixed-order reduction of the fp64 partials: block (32, 8) = 32 channels x 8 partial lanes.
+// Fixed-order reduction of the fp64 partials: block (32, 32) = 32 channels x 32 partial lanes, four
+// independent accumulators per lane so the L2 round trips overlap instead of chaining.
 __device__ __forceinline__ void reduce_parts(int C, const double* __restrict__ parts, int nparts, int ch,
                                              double& s, double& ss) {
-  __shared__ double r_a[8][32], r_b[8][32];
+  __shared__ double r_a[32][33], r_b[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  double a = 0.0, b = 0.0;
-  if (ch < C)
-    for (int p = ty; p < nparts; p += 8) { a += parts[(size_t)p * 2 * C + ch]; b += parts[(size_t)p * 2 * C + C + ch]; }
-  r_a[ty][tx] = a; r_b[ty][tx] = b;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+  if (ch < C) {
+    const size_t st = (size_t)2 * C;
+    int p = ty;
+    for (; p + 96 < nparts; p += 128) {
+      a0 += parts[(size_t)p * st + ch];          b0 += parts[(size_t)p * st + C + ch];
+      a1 += parts[(size_t)(p + 32) * st + ch];   b1 += parts[(size_t)(p + 32) * st + C + ch];
+      a2 += parts[(size_t)(p + 64) * st + ch];   b2 += parts[(size_t)(p + 64) * st + C + ch];
+      a3 += parts[(size_t)(p + 96) * st + ch];   b3 += parts[(size_t)(p + 96) * st + C + ch];
+    }
+    for (; p < nparts; p += 32) { a0 += parts[(size_t)p * st + ch]; b0 += parts[(size_t)p * st + C + ch]; }
+  }
+  r_a[ty][tx] = (a0 + a1) + (a2 + a3);
+  r_b[ty][tx] = (b0 + b1) + (b2 + b3);
   __syncthreads();
   s = 0.0; ss = 0.0;
   if (ty == 0) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) { s += r_a[r][tx]; ss += r_b[r][tx]; }
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) { s += r_a[r][tx]; ss += r_b[r][tx]; }
   }
 }
 
 // forward finalize
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double count,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ ema_mean, float* __restrict__ ema_var,
@@ -246,7 +257,7 @@ __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, co
 }
 
 // backward finalize: coef = [mean(dy) | mean(dy*yhat) | gamma*invstd]; dgamma = sum dy*yhat, dbeta = sum dy
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double count,
                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                        float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -362,6 +373,228 @@ __global__ void edge_unfold_wgrad_kernel(int c, int cout, const float* __restric
   }
 }
 
+// ---- float4 variants for the wide layers (C % 128 == 0, 16-byte aligned rows): a thread owns 4 channels,
+// keeps their per-channel constants in registers and streams rows with 4 loads in flight. ----
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+col_reduce_vec4_kernel(int R, int C, const float* __restrict__ Y, int ld, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, const float* __restrict__ dOut, int lddo, int group,
+                       float gscale, int relu, const int* __restrict__ argmax, double* __restrict__ parts) {
+  __shared__ double s_a[8][128], s_b[8][128];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * 128 + tx * 4;
+  const int r0 = blockIdx.y * COL_ROWS, r1 = min(R, r0 + COL_ROWS);
+  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  float4 sc, sh, mu, is;
+  if (MODE == 1) { sc = ld4(scale + ch); sh = ld4(shift + ch); mu = ld4(mean + ch); is = ld4(invstd + ch); }
+  for (int r = r0 + ty; r < r1; r += 32) {
+    float4 y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) y[u] = (r + 8 * u < r1) ? ld4(Y + (size_t)(r + 8 * u) * ld + ch) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + 8 * u;
+      if (rr >= r1) break;
+      const float yv[4] = {y[u].x, y[u].y, y[u].z, y[u].w};
+      if (MODE == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { a[c] += (double)yv[c]; b[c] += (double)yv[c] * (double)yv[c]; }
+      } else {
+        const int gr = rr / group;
+        const float4 g4 = ld4(dOut + (size_t)gr * lddo + ch);
+        const float gv[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+        const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+        int am[4] = {0, 0, 0, 0};
+        if (argmax != nullptr) {
+          const int4 t = *reinterpret_cast<const int4*>(argmax + (size_t)gr * C + ch);
+          am[0] = t.x; am[1] = t.y; am[2] = t.z; am[3] = t.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          bool on = !relu || fmaf(yv[c], scv[c], shv[c]) > 0.f;
+          if (argmax != nullptr) on = on && (am[c] == rr - gr * group);
+          if (on) { a[c] += (double)gv[c]; b[c] += (double)gv[c] * (double)((yv[c] - muv[c]) * isv[c]); }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { s_a[ty][tx * 4 + c] = a[c]; s_b[ty][tx * 4 + c] = b[c]; }
+  __syncthreads();
+  const int t = ty * 32 + tx;
+  if (t < 128) {
+    double sa = 0.0, sb = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { sa += s_a[r][t]; sb += s_b[r][t]; }
+    parts[(size_t)blockIdx.y * 2 * C + blockIdx.x * 128 + t] = sa;
+    parts[(size_t)blockIdx.y * 2 * C + C + blockIdx.x * 128 + t] = sb;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_bwd_vec4_kernel(int R, int C, const float* Y, int ld, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, const float* __restrict__ coef,
+                       const float* __restrict__ dOut, int lddo, int group, float gscale, int relu,
+                       const int* __restrict__ argmax, float* dY, int lddy) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * 128 + tx * 4;
+  const int r0 = blockIdx.y * COL_ROWS, r1 = min(R, r0 + COL_ROWS);
+  const float4 sc = ld4(scale + ch), sh = ld4(shift + ch), mu = ld4(mean + ch), is = ld4(invstd + ch);
+  const float4 c0 = ld4(coef + ch), c1 = ld4(coef + C + ch), c2 = ld4(coef + 2 * C + ch);
+  const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+  const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+  const float mdy[4] = {c0.x, c0.y, c0.z, c0.w}, mdz[4] = {c1.x, c1.y, c1.z, c1.w}, gis[4] = {c2.x, c2.y, c2.z, c2.w};
+  for (int r = r0 + ty; r < r1; r += 32) {
+    float4 y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) y[u] = (r + 8 * u < r1) ? ld4(Y + (size_t)(r + 8 * u) * ld + ch) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + 8 * u;
+      if (rr >= r1) break;
+      const int gr = rr / group;
+      const float4 g4 = ld4(dOut + (size_t)gr * lddo + ch);
+      const float gv[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+      const float yv[4] = {y[u].x, y[u].y, y[u].z, y[u].w};
+      int am[4] = {0, 0, 0, 0};
+      if (argmax != nullptr) {
+        const int4 t = *reinterpret_cast<const int4*>(argmax + (size_t)gr * C + ch);
+        am[0] = t.x; am[1] = t.y; am[2] = t.z; am[3] = t.w;
+      }
+      float o[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        bool on = !relu || fmaf(yv[c], scv[c], shv[c]) > 0.f;
+        if (argmax != nullptr) on = on && (am[c] == rr - gr * group);
+        const float dy = on ? gv[c] : 0.f;
+        o[c] = gis[c] * (dy - mdy[c] - (yv[c] - muv[c]) * isv[c] * mdz[c]);
+      }
+      *reinterpret_cast<float4*>(dY + (size_t)rr * lddy + ch) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+static inline bool vec4_ok(int C, const void* p0, int ld0, const void* p1, int ld1, const void* p2, int ld2) {
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (C % 128 == 0) && (ld0 % 4 == 0) && (ld1 % 4 == 0) && (ld2 % 4 == 0) && al(p0) && al(p1) && al(p2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cloud-resident EdgeConv kernels.  A CTA owns 64 output channels of ONE cloud: the cloud's Q rows
+// for those channels (n x 64 fp32 = 64 KB at n = 256) and its neighbour table are staged in shared
+// memory once, so the k-fold neighbour gather never leaves the SM; the backward scatter
+// dQ[nn(i,j)] += dz_ij accumulates in shared memory too (no global atomics, no zero-fill pass).
+// One fp64 partial row per cloud.  MODE: 0 stats, 1 apply, 2 backward reduce, 3 backward apply.
+constexpr int ES_CH = 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq, const int* __restrict__ idx,
+                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, const float* __restrict__ coef, const float* __restrict__ dOut,
+                  int lddo, float* __restrict__ out, int ldo, double* __restrict__ parts) {
+  extern __shared__ __align__(16) float es_smem[];
+  float* Qs = es_smem;                                   // [n][ES_CH]
+  float* dQs = Qs + (size_t)n * ES_CH;                   // [n][ES_CH] (MODE 3 only)
+  int* s_idx = reinterpret_cast<int*>(MODE == 3 ? dQs + (size_t)n * ES_CH : dQs);  // [n*k]
+  __shared__ double s_a[8][ES_CH], s_b[8][ES_CH];
+
+  const int cloud = blockIdx.y, c0 = blockIdx.x * ES_CH;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  const size_t base = (size_t)cloud * n;
+  for (int e = tid; e < n * (ES_CH / 4); e += 256) {
+    const int r = e / (ES_CH / 4), q = e - r * (ES_CH / 4);
+    *reinterpret_cast<float4*>(Qs + r * ES_CH + q * 4) =
+        *reinterpret_cast<const float4*>(PQ + (base + r) * ldpq + cout + c0 + q * 4);
+    if (MODE == 3) *reinterpret_cast<float4*>(dQs + r * ES_CH + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int e = tid; e < n * k; e += 256) s_idx[e] = idx[base * k + e];
+  __syncthreads();
+
+  const float invk = 1.f / (float)k;
+#pragma unroll
+  for (int h = 0; h < ES_CH / 32; ++h) {
+    const int cl = tx + 32 * h, ch = c0 + cl;
+    float sc = 0.f, sh = 0.f, mu = 0.f, is = 0.f, mdy = 0.f, mdz = 0.f, gis = 0.f;
+    if (MODE >= 1) { sc = scale[ch]; sh = shift[ch]; }
+    if (MODE >= 2) { mu = mean[ch]; is = invstd[ch]; }
+    if (MODE == 3) { mdy = coef[ch]; mdz = coef[cout + ch]; gis = coef[2 * cout + ch]; }
+    double a = 0.0, b = 0.0;
+    for (int p = ty; p < n; p += 8) {
+      const float pv = PQ[(base + p) * ldpq + ch];
+      float g = 0.f, acc = 0.f;
+      if (MODE >= 2) g = dOut[(base + p) * lddo + ch] * invk;
+      const int* nb = s_idx + p * k;
+      for (int j = 0; j < k; ++j) {
+        const int q = nb[j];
+        const float z = pv + Qs[q * ES_CH + cl];
+        if (MODE == 0) {
+          a += (double)z; b += (double)z * (double)z;
+        } else if (MODE == 1) {
+          acc += fmaxf(fmaf(z, sc, sh), 0.f);
+        } else if (MODE == 2) {
+          if (fmaf(z, sc, sh) > 0.f) { a += (double)g; b += (double)g * (double)((z - mu) * is); }
+        } else {
+          const float dy = (fmaf(z, sc, sh) > 0.f) ? g : 0.f;
+          const float dz = gis * (dy - mdy - (z - mu) * is * mdz);
+          acc += dz;
+          atomicAdd(dQs + q * ES_CH + cl, dz);
+        }
+      }
+      if (MODE == 1) out[(base + p) * ldo + ch] = acc * invk;
+      if (MODE == 3) out[(base + p) * ldo + ch] = acc;  // dP
+    }
+    if (MODE == 0 || MODE == 2) { s_a[ty][cl] = a; s_b[ty][cl] = b; }
+  }
+  if (MODE == 0 || MODE == 2) {
+    __syncthreads();
+    if (tid < ES_CH) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { a += s_a[r][tid]; b += s_b[r][tid]; }
+      parts[(size_t)cloud * 2 * cout + c0 + tid] = a;
+      parts[(size_t)cloud * 2 * cout + cout + c0 + tid] = b;
+    }
+  }
+  if (MODE == 3) {
+    __syncthreads();
+    for (int e = tid; e < n * (ES_CH / 4); e += 256) {
+      const int r = e / (ES_CH / 4), q = e - r * (ES_CH / 4);
+      *reinterpret_cast<float4*>(out + (base + r) * ldo + cout + c0 + q * 4) =
+          *reinterpret_cast<const float4*>(dQs + r * ES_CH + q * 4);
+    }
+  }
+}
+
+static inline size_t edge_cloud_smem(int n, int k, int mode) {
+  return sizeof(float) * (size_t)n * ES_CH * (mode == 3 ? 2 : 1) + sizeof(int) * (size_t)n * k;
+}
+// the cloud-resident kernels apply when a cloud's tile fits shared memory and rows are float4-addressable
+static inline bool edge_cloud_ok(int n, int k, int cout, int ldpq) {
+  return (cout % ES_CH == 0) && (ldpq % 4 == 0) && edge_cloud_smem(n, k, 3) <= 200 * 1024;
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int MODE>
+static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
+                             const float* scale, const float* shift, const float* mean, const float* invstd,
+                             const float* coef, const float* dOut, int lddo, float* out, int ldo, double* parts,
+                             cudaStream_t s) {
+  const size_t smem = edge_cloud_smem(n, k, MODE);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(edge_cloud_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  edge_cloud_kernel<MODE><<<dim3(cout / ES_CH, b), dim3(32, 8), smem, s>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean,
+                                                                          invstd, coef, dOut, lddo, out, ldo, parts);
+  return CAAE_LAUNCH_STATUS();
+}
+
 static inline int flat_blocks(long total) {
   long blocks = (total + 255) / 256;
   const long cap = (long)kNumSMs * 16;
@@ -373,7 +606,11 @@ static inline int flat_blocks(long total) {
 using namespace caae;
 
 // ---- EdgeConv -------------------------------------------------------------------------------
-extern "C" int caae_edge_parts(int b, int n) { return b * ((n + EDGE_PTS - 1) / EDGE_PTS); }
+// Number of fp64 partial rows caae_edge_stats / caae_edge_bwd_reduce write for this shape: one per
+// cloud on the cloud-resident path, one per 32-point chunk otherwise.
+extern "C" int caae_edge_parts(int b, int n, int k, int cout, int ldpq) {
+  return edge_cloud_ok(n, k, cout, ldpq) ? b : b * ((n + EDGE_PTS - 1) / EDGE_PTS);
+}
 
 static int edge_args_ok(int b, int n, int k, int cout) {
   return !(b < 0 || n <= 0 || k <= 0 || k > 32 || cout <= 0 || (cout % 32) != 0 || b > 65535);
@@ -384,6 +621,11 @@ extern "C" int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, i
   CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!PQ || !idx || !parts, CAAE_E_NULLPTR);
+  if (edge_cloud_ok(n, k, cout, ldpq)) {
+    CAAE_RETURN_IF(!aligned16(PQ), CAAE_E_UNSUPPORTED);
+    return launch_edge_cloud<0>(b, n, k, cout, PQ, ldpq, idx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                                nullptr, 0, parts, as_stream(stream));
+  }
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
   edge_reduce_kernel<0><<<grid, block, 0, as_stream(stream)>>>(n, k, cout, PQ, ldpq, idx, nullptr, nullptr, nullptr,
                                                                 nullptr, nullptr, 0, parts);
@@ -395,6 +637,11 @@ extern "C" int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, i
   CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout || ldo < cout, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!PQ || !idx || !scale || !shift || !out, CAAE_E_NULLPTR);
+  if (edge_cloud_ok(n, k, cout, ldpq)) {
+    CAAE_RETURN_IF(!aligned16(PQ), CAAE_E_UNSUPPORTED);
+    return launch_edge_cloud<1>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out,
+                                ldo, nullptr, as_stream(stream));
+  }
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
   edge_apply_kernel<<<grid, block, 0, as_stream(stream)>>>(n, k, cout, PQ, ldpq, idx, scale, shift, out, ldo);
   return CAAE_LAUNCH_STATUS();
@@ -406,6 +653,11 @@ extern "C" int caae_edge_bwd_reduce(int b, int n, int k, int cout, const float* 
   CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout || lddo < cout, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!PQ || !idx || !scale || !shift || !mean || !invstd || !dOut || !parts, CAAE_E_NULLPTR);
+  if (edge_cloud_ok(n, k, cout, ldpq)) {
+    CAAE_RETURN_IF(!aligned16(PQ), CAAE_E_UNSUPPORTED);
+    return launch_edge_cloud<2>(b, n, k, cout, PQ, ldpq, idx, scale, shift, mean, invstd, nullptr, dOut, lddo, nullptr,
+                                0, parts, as_stream(stream));
+  }
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
   edge_reduce_kernel<1><<<grid, block, 0, as_stream(stream)>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean, invstd,
                                                                 dOut, lddo, parts);
@@ -420,6 +672,11 @@ extern "C" int caae_edge_bwd_apply(int b, int n, int k, int cout, const float* P
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!PQ || !idx || !scale || !shift || !mean || !invstd || !coef || !dOut || !dPQ, CAAE_E_NULLPTR);
   cudaStream_t s = as_stream(stream);
+  if (edge_cloud_ok(n, k, cout, ldpq) && lddpq % 4 == 0) {
+    CAAE_RETURN_IF(!aligned16(PQ) || !aligned16(dPQ), CAAE_E_UNSUPPORTED);
+    return launch_edge_cloud<3>(b, n, k, cout, PQ, ldpq, idx, scale, shift, mean, invstd, coef, dOut, lddo, dPQ, lddpq,
+                                nullptr, s);
+  }
   cudaError_t e = cudaMemset2DAsync(dPQ, sizeof(float) * (size_t)lddpq, 0, sizeof(float) * 2 * (size_t)cout,
                                     (size_t)b * n, s);
   if (e != cudaSuccess) return (int)e;
@@ -437,6 +694,12 @@ extern "C" int caae_col_stats(int R, int C, const float* Y, int ld, double* part
   CAAE_RETURN_IF(!Y || !parts, CAAE_E_NULLPTR);
   dim3 grid((C + 31) / 32, (R + COL_ROWS - 1) / COL_ROWS), block(32, 8);
   CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
+  if (vec4_ok(C, Y, ld, nullptr, 0, nullptr, 0)) {
+    grid.x = C / 128;
+    col_reduce_vec4_kernel<0><<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, nullptr, nullptr, nullptr, nullptr,
+                                                                      nullptr, 0, 1, 1.f, 0, nullptr, parts);
+    return CAAE_LAUNCH_STATUS();
+  }
   col_reduce_kernel<0><<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                0, 1, 1.f, 0, nullptr, parts);
   return CAAE_LAUNCH_STATUS();
@@ -448,7 +711,7 @@ extern "C" int caae_bn_finalize(int C, const double* parts, int nparts, double c
                                 caae_stream_t stream) {
   CAAE_RETURN_IF(C <= 0 || nparts <= 0 || count <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!parts || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd, CAAE_E_NULLPTR);
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, beta, ema_mean,
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, beta, ema_mean,
                                                                      ema_var, decay, scale, shift, save_mean,
                                                                      save_invstd);
   return CAAE_LAUNCH_STATUS();
@@ -467,7 +730,7 @@ extern "C" int caae_bn_bwd_finalize(int C, const double* parts, int nparts, doub
                                     caae_stream_t stream) {
   CAAE_RETURN_IF(C <= 0 || nparts <= 0 || count <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!parts || !gamma || !invstd || !coef || !dgamma || !dbeta, CAAE_E_NULLPTR);
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, invstd, coef,
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, invstd, coef,
                                                                          dgamma, dbeta);
   return CAAE_LAUNCH_STATUS();
 }
@@ -499,6 +762,12 @@ extern "C" int caae_bn_act_bwd_reduce(int R, int C, const float* Y, int ld, cons
   CAAE_RETURN_IF(!Y || !scale || !shift || !mean || !invstd || !dOut || !parts, CAAE_E_NULLPTR);
   dim3 grid((C + 31) / 32, (R + COL_ROWS - 1) / COL_ROWS), block(32, 8);
   CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
+  if (vec4_ok(C, Y, ld, dOut, lddo, nullptr, 0)) {
+    grid.x = C / 128;
+    col_reduce_vec4_kernel<1><<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, scale, shift, mean, invstd, dOut,
+                                                                      lddo, group, gscale, relu, argmax, parts);
+    return CAAE_LAUNCH_STATUS();
+  }
   col_reduce_kernel<1><<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, scale, shift, mean, invstd, dOut, lddo,
                                                                group, gscale, relu, argmax, parts);
   return CAAE_LAUNCH_STATUS();
@@ -510,6 +779,13 @@ extern "C" int caae_bn_act_bwd_apply(int R, int C, const float* Y, int ld, const
                                      int lddy, caae_stream_t stream) {
   CAAE_RETURN_IF(R <= 0 || C <= 0 || ld < C || lddo < C || lddy < C || group <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!Y || !scale || !shift || !mean || !invstd || !coef || !dOut || !dY, CAAE_E_NULLPTR);
+  if (vec4_ok(C, Y, ld, dOut, lddo, dY, lddy)) {
+    dim3 grid(C / 128, (R + COL_ROWS - 1) / COL_ROWS), block(32, 8);
+    CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
+    bn_act_bwd_vec4_kernel<<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, scale, shift, mean, invstd, coef, dOut,
+                                                                   lddo, group, gscale, relu, argmax, dY, lddy);
+    return CAAE_LAUNCH_STATUS();
+  }
   const long total = (long)R * C;
   bn_act_bwd_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(total, C, Y, ld, scale, shift, mean, invstd,
                                                                        coef, dOut, lddo, group, gscale, relu, argmax,

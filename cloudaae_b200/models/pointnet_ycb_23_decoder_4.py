@@ -161,7 +161,7 @@ class _Engine:
             if bn:
                 self.bn[s] = {k_: torch.empty(fout, **f32) for k_ in ("scale", "shift", "mean", "invstd")}
                 self.bn[s]["coef"] = torch.empty(3 * fout, **f32)
-        nparts = max(self.lib.caae_edge_parts(B, num_point), self.lib.caae_col_parts(R), 1)
+        nparts = max(B * ((num_point + 31) // 32), self.lib.caae_col_parts(R), 1)
         self.parts = torch.empty(nparts * 2 * 1024, dtype=torch.float64, device=self.dev)
         self.default_decay = torch.full((1,), 0.9, **f32)  # tf_util.py:494: decay defaults to 0.9
         self.decay_scalar = torch.empty(1, **f32)
@@ -295,7 +295,7 @@ class _Engine:
                 if train_enc:
                     self._c("caae_edge_stats", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
                             self._p(self.parts))
-                self._bn_coeffs(scope, train_enc, self.lib.caae_edge_parts(B, N), R * k, decay)
+                self._bn_coeffs(scope, train_enc, self.lib.caae_edge_parts(B, N, k, co, 2 * co), R * k, decay)
                 out = self.hcat[:, self.offs[l]:]
                 bn = self.bn[scope]
                 self._c("caae_edge_apply", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
@@ -369,7 +369,7 @@ class _Engine:
                 args = (B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]), self._p(bn["scale"]),
                         self._p(bn["shift"]), self._p(bn["mean"]), self._p(bn["invstd"]))
                 self._c("caae_edge_bwd_reduce", *args, self._p(d_out), 320, self._p(self.parts))
-                self._c("caae_bn_bwd_finalize", co, self._p(self.parts), self.lib.caae_edge_parts(B, N), float(R * k),
+                self._c("caae_bn_bwd_finalize", co, self._p(self.parts), self.lib.caae_edge_parts(B, N, k, co, 2 * co), float(R * k),
                         self._p(self.v[f"{scope}/bn/gamma"]), self._p(bn["invstd"]), self._p(bn["coef"]),
                         self._p(self.v.grad_of(f"{scope}/bn/gamma")), self._p(self.v.grad_of(f"{scope}/bn/beta")))
                 self._c("caae_edge_bwd_apply", *args, self._p(bn["coef"]), self._p(d_out), 320, self._p(self.d_pq),

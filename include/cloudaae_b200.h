@@ -106,7 +106,7 @@ int caae_gemm_tf32_supported(int transa, int transb, int M, int N, int K, const 
 int caae_knn(int b, int n, int c, int k, const float* x, int ldx, int* idx, caae_stream_t stream);
 
 /* EdgeConv on the factorised projection PQ [b*n, >=2*cout] = [P | Q]: z_ij = P_i + Q_nn(i,j). */
-int caae_edge_parts(int b, int n); /* number of fp64 partial rows caae_edge_stats / _bwd_reduce write */
+int caae_edge_parts(int b, int n, int k, int cout, int ldpq); /* fp64 partial rows caae_edge_stats / _bwd_reduce write */
 int caae_edge_fold_weights(int c, int cout, const float* w, const float* bias, float* wf, float* bias_f, int ldw,
                            caae_stream_t stream);
 int caae_edge_unfold_wgrad(int c, int cout, const float* dwf, int lddwf, float* dw, caae_stream_t stream);
