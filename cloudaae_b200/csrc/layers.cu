@@ -493,7 +493,7 @@ static inline bool vec4_ok(int C, const void* p0, int ld0, const void* p1, int l
 constexpr int ES_CH = 64;
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq, const int* __restrict__ idx,
                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef, const float* __restrict__ dOut,
@@ -502,18 +502,18 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
   float* Qs = es_smem;                                   // [n][ES_CH]
   float* dQs = Qs + (size_t)n * ES_CH;                   // [n][ES_CH] (MODE 3 only)
   int* s_idx = reinterpret_cast<int*>(MODE == 3 ? dQs + (size_t)n * ES_CH : dQs);  // [n*k]
-  __shared__ double s_a[8][ES_CH], s_b[8][ES_CH];
+  __shared__ double s_a[32][ES_CH + 1], s_b[32][ES_CH + 1];
 
   const int cloud = blockIdx.y, c0 = blockIdx.x * ES_CH;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   const size_t base = (size_t)cloud * n;
-  for (int e = tid; e < n * (ES_CH / 4); e += 256) {
+  for (int e = tid; e < n * (ES_CH / 4); e += 1024) {
     const int r = e / (ES_CH / 4), q = e - r * (ES_CH / 4);
     *reinterpret_cast<float4*>(Qs + r * ES_CH + q * 4) =
         *reinterpret_cast<const float4*>(PQ + (base + r) * ldpq + cout + c0 + q * 4);
     if (MODE == 3) *reinterpret_cast<float4*>(dQs + r * ES_CH + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int e = tid; e < n * k; e += 256) s_idx[e] = idx[base * k + e];
+  for (int e = tid; e < n * k; e += 1024) s_idx[e] = idx[base * k + e];
   __syncthreads();
 
   const float invk = 1.f / (float)k;
@@ -525,7 +525,7 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
     if (MODE >= 2) { mu = mean[ch]; is = invstd[ch]; }
     if (MODE == 3) { mdy = coef[ch]; mdz = coef[cout + ch]; gis = coef[2 * cout + ch]; }
     double a = 0.0, b = 0.0;
-    for (int p = ty; p < n; p += 8) {
+    for (int p = ty; p < n; p += 32) {
       const float pv = PQ[(base + p) * ldpq + ch];
       float g = 0.f, acc = 0.f;
       if (MODE >= 2) g = dOut[(base + p) * lddo + ch] * invk;
@@ -555,15 +555,15 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
     __syncthreads();
     if (tid < ES_CH) {
       double a = 0.0, b = 0.0;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) { a += s_a[r][tid]; b += s_b[r][tid]; }
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) { a += s_a[r][tid]; b += s_b[r][tid]; }
       parts[(size_t)cloud * 2 * cout + c0 + tid] = a;
       parts[(size_t)cloud * 2 * cout + cout + c0 + tid] = b;
     }
   }
   if (MODE == 3) {
     __syncthreads();
-    for (int e = tid; e < n * (ES_CH / 4); e += 256) {
+    for (int e = tid; e < n * (ES_CH / 4); e += 1024) {
       const int r = e / (ES_CH / 4), q = e - r * (ES_CH / 4);
       *reinterpret_cast<float4*>(out + (base + r) * ldo + cout + c0 + q * 4) =
           *reinterpret_cast<const float4*>(dQs + r * ES_CH + q * 4);
@@ -590,7 +590,7 @@ static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int
     cudaError_t e = cudaFuncSetAttribute(edge_cloud_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  edge_cloud_kernel<MODE><<<dim3(cout / ES_CH, b), dim3(32, 8), smem, s>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean,
+  edge_cloud_kernel<MODE><<<dim3(cout / ES_CH, b), dim3(32, 32), smem, s>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean,
                                                                           invstd, coef, dOut, lddo, out, ldo, parts);
   return CAAE_LAUNCH_STATUS();
 }

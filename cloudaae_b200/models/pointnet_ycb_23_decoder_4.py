@@ -203,6 +203,7 @@ class _Engine:
                     self.fc_d[s] = torch.empty(B, fout, **f32)
         self.x0 = None
         self.trained = (False, False)
+        self.after_fc_backward = None
 
     # -- helpers
     def _st(self):
@@ -355,6 +356,8 @@ class _Engine:
             first = False
         if d_emb_extra is not None:
             self.d_emb.add_(d_emb_extra)
+        if self.after_fc_backward is not None:  # every FC / head gradient is final: start its allreduce
+            self.after_fc_backward()
         if self.model == "dgcnn":
             scope = "dgcnn_agg"
             # mean-pool + ReLU + BN backward, in place over the pre-activation

@@ -17,6 +17,7 @@ import torch
 
 from . import _capi
 from .models.pointnet_ycb_23_decoder_4 import NUM_CLASS, Variables, _Engine, dgcnn_layers, pn_layers
+from .parallel import BucketedAllReduce, broadcast_variables
 
 
 class CloudAAETrainer:
@@ -57,6 +58,15 @@ class CloudAAETrainer:
         self.losses = torch.zeros(4, **f32)  # total, chamfer, trans, rot
         self._graph = None
         self._static = None
+        # gradient exchange: bucket 1 = everything after the encoder (FC decoder + pose heads), complete
+        # as soon as the FC backward has run; bucket 0 = the encoder, complete at the end of backward.
+        enc_last = "dgcnn_agg" if model == "dgcnn" else "pn_conv5_encoder"
+        split = self.v.index[f"{enc_last}/bn/gamma"][0] + 1024
+        split = ((split + 31) // 32) * 32
+        self.reducer = BucketedAllReduce(self.v.grad, [0, split, self.v.grad.numel()], group=process_group)
+        self.engine.after_fc_backward = (lambda: self.reducer.start(1)) if self.world > 1 else None
+        if self.world > 1:
+            broadcast_variables(self.v.flat, self.v.ema, group=process_group)
 
     # ------------------------------------------------------------------
     def _st(self):
@@ -93,7 +103,8 @@ class CloudAAETrainer:
     def apply_gradients(self):
         p = _Engine._p
         if self.world > 1:
-            torch.distributed.all_reduce(self.v.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            self.reducer.start(0)
+            self.reducer.finish()
         self._c("caae_adam_tf", self.v.flat.numel(), p(self.v.flat), p(self.v.grad), p(self.adam_m), p(self.adam_v),
                 p(self.state), self.lr, self.beta1, self.beta2, self.eps, 1.0 / self.world)
 

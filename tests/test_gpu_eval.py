@@ -1,0 +1,108 @@
+"""Evaluation graph (evaluate_cloudAAE_ycbv.py:405-477), losses API and sharded batched inference."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import model_ref as MR
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+
+from cloudaae_b200.inference import CloudAAEInference, run_sharded  # noqa: E402
+from cloudaae_b200.losses import angular_distance_taylor, chamfer_loss, trans_distance  # noqa: E402
+from cloudaae_b200.models import pointnet_ycb_23_decoder_4 as M  # noqa: E402
+from test_gpu_model import _setup, rel_err  # noqa: E402
+
+
+@pytest.mark.parametrize("b", [1, 5])
+def test_eval_forward_matches_oracle_config1(b):
+    """BASELINE config 1: batch 1, class 0, one synthetic YCB segment at num_point 256 (and a batch of 5)."""
+    n = 256
+    v, p64, visible, target, cls, trans, axag, noise = _setup("dgcnn", b, n, seed=21)
+    if b == 1:
+        cls = torch.zeros(1, dtype=torch.int32)
+    seg = visible[:, :n].contiguous()
+    tgt = target[:, :n].contiguous()
+    inf = CloudAAEInference(v, batch_size=b, num_point=n, precision="fp32")
+    out = inf.forward(seg.cuda(), cls.cuda(), tgt.cuda(), trans.cuda(), axag.cuda())
+    torch.cuda.synchronize()
+    # oracle: same graph in float64, neighbour indices injected
+    x64, mean64 = MR.prepare_input(seg.double(), cls, torch.zeros(b, n, 3, dtype=torch.float64), num_point=n)
+    override = [i.view(b, n, -1).cpu().long() for i in inf.engine.idx]
+    r64, rot64, t64, _ = MR.get_model_dgcnn_mean_6d(x64, p64, False, False, 10, nn_idx_override=override)
+    recon64 = r64 + mean64[:, None]
+    assert rel_err(out["recon"], recon64) < 1e-3
+    assert rel_err(out["rot_pred"], rot64) < 1e-3 and rel_err(out["trans_pred"], t64 + mean64) < 1e-3
+    # FPS 1024 -> 256 + gather on the kernel's own reconstruction: bit-exact vs the oracle
+    recon = out["recon"].cpu().numpy()
+    oidx = O.fps(recon, n)
+    assert (out["fps_idx"].cpu().numpy() == oidx).all()
+    osub = O.gather(recon, oidx)
+    assert (out["recon_fps"].cpu().numpy() == osub).all()
+    od1, oi1, od2, oi2 = O.nn_distance(osub, tgt.numpy(), "gpu")
+    assert (inf.idx1.cpu().numpy() == oi1).all() and (inf.idx2.cpu().numpy() == oi2).all()
+    assert (out["chamfer"].cpu().numpy() == od1 + od2).all()
+    # pose errors
+    _, terr = MR.get_translation_error(t64 + mean64, trans.double())
+    _, rerr = MR.get_rotation_error(rot64, axag.double())
+    assert rel_err(out["trans_err"], terr) < 1e-3 and rel_err(out["rot_err"], rerr) < 1e-3
+
+
+def test_losses_api_values_and_gradients():
+    g = torch.Generator().manual_seed(4)
+    b = 16
+    pred = torch.randn(b, 3, generator=g); label = torch.randn(b, 3, generator=g)
+    # include small-angle (Taylor branch) and near-identical (clipped acos) cases
+    pred[0] = torch.tensor([1e-3, -2e-3, 5e-4]); label[1] = pred[1].clone()
+    pc = pred.cuda().requires_grad_(True)
+    loss, per = angular_distance_taylor.get_rotation_error(pc.double(), label.cuda().double())
+    assert per.dtype == torch.float64
+    loss.backward()
+    p64 = pred.double().requires_grad_(True)
+    l64, per64 = MR.get_rotation_error(p64, label.double())
+    l64.backward()
+    assert rel_err(per, per64) < 1e-9 and abs(loss.item() - l64.item()) < 1e-12
+    assert rel_err(pc.grad, p64.grad) < 1e-6
+    tp = pred.cuda().requires_grad_(True)
+    tl, tper = trans_distance.get_translation_error(tp, label.cuda())
+    tl.backward()
+    t64 = pred.double().requires_grad_(True)
+    tl64, tper64 = MR.get_translation_error(t64, label.double())
+    tl64.backward()
+    assert rel_err(tper, tper64) < 1e-6 and rel_err(tp.grad, t64.grad) < 1e-5
+    # exponential_map helper == oracle
+    R = angular_distance_taylor.exponential_map(pred.double().cuda())
+    assert rel_err(R, MR.exponential_map(pred.double())) < 1e-12
+    # chamfer get_loss
+    x = torch.from_numpy(cases.random_clouds(1, 3, 256)).cuda().requires_grad_(True)
+    y = torch.from_numpy(cases.random_clouds(2, 3, 256)).cuda()
+    closs, cper = chamfer_loss.get_loss(x, y)
+    closs.backward()
+    x64 = x.detach().cpu().double().requires_grad_(True)
+    c64, cper64 = MR.chamfer_get_loss(x64, y.cpu().double())
+    c64.backward()
+    assert rel_err(cper, cper64) < 1e-5 and rel_err(x.grad, x64.grad) < 1e-5
+    with pytest.raises(ValueError):
+        chamfer_loss.get_loss(x, y[:, :100].contiguous())
+
+
+def test_sharded_inference_equals_single_rank():
+    n, total, bsz = 256, 37, 8
+    v, *_ = _setup("dgcnn", bsz, n, seed=31)
+    rng = np.random.default_rng(5)
+    clouds = cases.posed_ycb_clouds(2)[rng.integers(0, 21, total)]
+    seg = torch.from_numpy(np.ascontiguousarray(clouds[:, :n])).cuda()
+    tgt = torch.from_numpy(np.ascontiguousarray(clouds[:, 100:100 + n])).cuda()
+    cls = torch.from_numpy(rng.integers(0, 21, total).astype(np.int32)).cuda()
+    t, a, _ = cases.ycb_poses()
+    tr = torch.from_numpy(t[:total]).cuda(); ax = torch.from_numpy(a[:total]).cuda()
+    inf = CloudAAEInference(v, batch_size=bsz, num_point=n)
+    s0, e0, c_all, t_all, r_all = run_sharded(inf, seg, cls, tgt, tr, ax, 0, 1)
+    assert (s0, e0) == (0, total) and c_all.shape == (total,)
+    parts = [run_sharded(inf, seg, cls, tgt, tr, ax, r, 3) for r in range(3)]
+    assert [p[0] for p in parts] == [0, 13, 25] and parts[-1][1] == total
+    # eval-mode BN: a segment's result does not depend on which batch / rank it lands in
+    assert torch.allclose(torch.cat([p[2] for p in parts]), c_all, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(torch.cat([p[3] for p in parts]), t_all, rtol=1e-5)
+    assert torch.allclose(torch.cat([p[4] for p in parts]), r_all, rtol=1e-5)
