@@ -29,7 +29,8 @@ class CloudAAENativeError(RuntimeError):
 
 # name -> argument codes (i = int, l = long, f = float, d = double, p = pointer / stream handle).
 # Every entry point returns an int status unless listed in _SPECIAL.
-_CODES = {"i": _int, "l": ctypes.c_long, "f": ctypes.c_float, "d": ctypes.c_double, "p": _ptr}
+_CODES = {"i": _int, "l": ctypes.c_long, "f": ctypes.c_float, "d": ctypes.c_double, "p": _ptr,
+          "Q": ctypes.c_ulonglong}
 _SIGNATURES = {
     # tf_ops drop-ins
     "caae_fps": "iiipppp",
@@ -66,6 +67,10 @@ _SIGNATURES = {
     "caae_step_begin": "pi" "p",
     "caae_adam_tf": "lpppppfffff" "p",
     "caae_fill_f32": "lpf" "p",
+    # on-line synthesis
+    "caae_philox_fill": "lpQipi" "p",
+    "caae_synth_points": "iiippppppffffppp" "p",
+    "caae_hpr_select": "iippiipppp" "p",
 }
 _SIGNATURES = {k: [_CODES[c] for c in v] for k, v in _SIGNATURES.items()}
 _SPECIAL = {

@@ -162,6 +162,32 @@ int caae_adam_tf(long n, float* p, const float* g, float* m, float* v, const int
                  float beta2, float eps, float grad_scale, caae_stream_t stream);
 int caae_fill_f32(long n, float* p, float value, caae_stream_t stream);
 
+/* ==== on-line segment synthesis ================================================================
+ * train_cloudAAE_ycbv.py:79-93 (pose transform), utils/generate_occluder.py:38-81 (spherical occluders),
+ * utils/hidden_point_removal.py:6-73 (spherical flip, Qhull visibility, padding).  Random draws are
+ * explicit inputs (standard normals / uniforms), produced on the device by caae_philox_fill. */
+
+/* out[i] ~ N(0,1) (uniform = 0) or U(0,1) (uniform = 1); Philox4x32-10 keyed by seed, counter
+ * (i/4, stream_id, *offset); offset is a device int so CUDA-graph replays draw fresh numbers. */
+int caae_philox_fill(long n, float* out, unsigned long long seed, int stream_id, const int* offset, int uniform,
+                     caae_stream_t stream);
+
+/* models f32[num_class, nm, 3]; per sample: points[b, nm+no, 3] = model[class] R(axisangle)^T + translation
+ * followed by no occluder points (two N(centre, 0.01) blobs, rows alternating); flip_all f32[b, nm+no, 3]
+ * and flip_org f32[b, nm, 3] are the spherical flips about the origin (radius max|p| * flip_pow). */
+int caae_synth_points(int b, int nm, int no, const float* models, const int* class_id, const float* axisangle,
+                      const float* translation, const float* z_centers, const float* z_points, float hnear,
+                      float wnear, float near_dist, float flip_pow, float* points, float* flip_all, float* flip_org,
+                      caae_stream_t stream);
+
+/* Hidden point removal on flipped f32[b,n,3] (the viewpoint/origin row is implicit) + convexHull()'s
+ * selection: visible ids ascending, the highest one dropped, first `take` rows of org gathered into
+ * out_pts f32[b,take,3], short sets padded by picks pad_uniform f32[b,take] in [0,1) (NULL: cyclic).
+ * num_vis i32[b] = visible count after the drop; flags_out u8[b,n] (optional) = hull-vertex flags. */
+int caae_hpr_select(int b, int n, const float* flipped, const float* org, int org_stride_pts, int take,
+                    const float* pad_uniform, float* out_pts, int* num_vis, unsigned char* flags_out,
+                    caae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

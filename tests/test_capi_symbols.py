@@ -76,6 +76,8 @@ def _header_prototypes():
                     codes += "p"
                 elif a.startswith("int "):
                     codes += "i"
+                elif a.startswith("unsigned long long "):
+                    codes += "Q"
                 elif a.startswith("long "):
                     codes += "l"
                 elif a.startswith("float "):
@@ -91,7 +93,7 @@ def _header_prototypes():
 def test_ctypes_signatures_match_the_header():
     import ctypes as C
     from cloudaae_b200 import _capi
-    back = {C.c_int: "i", C.c_long: "l", C.c_float: "f", C.c_double: "d", C.c_void_p: "p"}
+    back = {C.c_int: "i", C.c_long: "l", C.c_float: "f", C.c_double: "d", C.c_void_p: "p", C.c_ulonglong: "Q"}
     protos = _header_prototypes()
     for name, argtypes in _capi._SIGNATURES.items():
         got = "".join(back[a] for a in argtypes)

@@ -1,0 +1,145 @@
+"""On-line segment synthesis on the GPU vs the NumPy/SciPy restatement (oracle/synthesis.py), whose
+hull is scipy.spatial.ConvexHull — the very call the reference makes (utils/hidden_point_removal.py:32)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import synthesis as S
+
+pytestmark = pytest.mark.gpu
+
+from cloudaae_b200 import _capi  # noqa: E402
+from cloudaae_b200.synthesis import SegmentSynthesizer, load_models_xyz  # noqa: E402
+from cloudaae_b200.utils import generate_occluder, hidden_point_removal as HPR  # noqa: E402
+
+
+def _poses(b, seed):
+    t, a, c = cases.ycb_poses()
+    sel = np.random.default_rng(seed).integers(0, len(c), b)
+    return c[sel].astype(np.int32), a[sel], t[sel]
+
+
+def test_philox_normals_and_uniforms():
+    lib = _capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    n = 1 << 20
+    off = torch.zeros(1, dtype=torch.int32, device="cuda")
+    a = torch.empty(n, device="cuda"); b = torch.empty(n, device="cuda"); u = torch.empty(n + 3, device="cuda")
+    _capi.check(lib.caae_philox_fill(n, a.data_ptr(), 7, 1, off.data_ptr(), 0, st), "philox")
+    _capi.check(lib.caae_philox_fill(n, b.data_ptr(), 7, 1, off.data_ptr(), 0, st), "philox")
+    assert torch.equal(a, b)                                   # same (seed, stream, offset) -> same draws
+    assert abs(a.mean().item()) < 5e-3 and abs(a.var().item() - 1) < 1e-2
+    assert abs((a ** 4).mean().item() - 3) < 0.1              # normal kurtosis
+    off += 1
+    _capi.check(lib.caae_philox_fill(n, b.data_ptr(), 7, 1, off.data_ptr(), 0, st), "philox")
+    assert not torch.equal(a, b) and abs((a * b).mean().item()) < 5e-3
+    _capi.check(lib.caae_philox_fill(n + 3, u.data_ptr(), 7, 2, off.data_ptr(), 1, st), "philox")
+    assert u.min().item() > 0 and u.max().item() < 1 and abs(u.mean().item() - 0.5) < 2e-3
+
+
+def test_pose_transform_occluder_and_flip_match_oracle():
+    b = 16
+    cls, ax, tr = _poses(b, 3)
+    rng = np.random.default_rng(4)
+    zc = rng.standard_normal((b, 2, 3)).astype(np.float32)
+    zp = rng.standard_normal((b, 2, 200, 3)).astype(np.float32)
+    models = cases.ycb_models()
+    syn = SegmentSynthesizer(torch.from_numpy(models).cuda(), b)
+    syn.z_centers.copy_(torch.from_numpy(zc)); syn.z_points.copy_(torch.from_numpy(zp))
+    syn.synthesize(torch.from_numpy(cls).cuda(), torch.from_numpy(ax).cuda(), torch.from_numpy(tr).cuda(), draw=False)
+    torch.cuda.synchronize()
+    P = S.transform_object_model(models[cls], ax, tr)
+    occ = S.spherical_occluder(tr[:, 2], zc, zp)
+    pts = np.concatenate([P, occ], 1)
+    got = syn.points.cpu().numpy()
+    assert np.abs(got[:, :2048] - P).max() < 2e-7 * np.abs(P).max() + 1e-7
+    assert (got[:, 2048:] == occ).all()                        # occluder arithmetic is bit-exact
+    assert (generate_occluder.get_random_spherical_occluder(torch.from_numpy(tr).cuda(), "ycbv", torch.from_numpy(zc).cuda(),
+                                                            torch.from_numpy(zp).cuda()).cpu().numpy() == occ).all()
+    # flips: evaluate the oracle on the kernel's own points so only the flip arithmetic is compared
+    fl_all, _ = S.spherical_flip(got)
+    fl_org, _ = S.spherical_flip(got[:, :2048])
+    assert (syn.flip_all.cpu().numpy() == fl_all[:, :-1]).all()
+    assert (syn.flip_org.cpu().numpy() == fl_org[:, :-1]).all()
+    f2, o2 = HPR.sphericalFlip(torch.from_numpy(got).cuda())
+    assert np.abs(f2.cpu().numpy() - fl_all).max() <= 2e-7 * np.abs(fl_all).max()
+    assert (o2[:, -1] == 0).all() and (f2[:, -1] == 0).all()
+
+
+@pytest.mark.parametrize("variant", ["occluded", "org"])
+def test_hidden_point_removal_matches_qhull(variant):
+    b = 24
+    cls, ax, tr = _poses(b, 5)
+    rng = np.random.default_rng(6)
+    P = S.transform_object_model(cases.ycb_models()[cls], ax, tr)
+    if variant == "occluded":
+        occ = S.spherical_occluder(tr[:, 2], rng.standard_normal((b, 2, 3)), rng.standard_normal((b, 2, 200, 3)))
+        pts = np.concatenate([P, occ], 1)
+    else:
+        pts = P
+    flipped, org = S.spherical_flip(pts)
+    want_pts, want_num, want_ids = S.convex_hull_visible(flipped, org)      # scipy / Qhull
+    vis, num, flags = HPR.convexHull(torch.from_numpy(flipped).cuda(), torch.from_numpy(org).cuda(), return_flags=True)
+    flags = flags.cpu().numpy().astype(bool)
+    inter = union = 0
+    for k in range(b):
+        from scipy.spatial import ConvexHull
+        hv = np.zeros(flags.shape[1], bool)
+        hv[np.sort(ConvexHull(flipped[k].astype(np.float64)).vertices)[:-1]] = True
+        inter += (hv & flags[k]).sum(); union += (hv | flags[k]).sum()
+    iou = inter / union
+    print(f"HPR visible-set IoU vs Qhull ({variant}): {iou:.6f}")
+    assert iou >= 0.995                                         # SURVEY §7 hard part 1; measured 1.0
+    same = [k for k in range(b) if (np.where(flags[k])[0][:-1] == want_ids[k]).all() if flags[k].sum() - 1 == len(want_ids[k])]
+    assert len(same) >= b - 1
+    assert (num.cpu().numpy()[same] == want_num[same]).all()
+    assert (vis.cpu().numpy()[same] == want_pts[same]).all()    # ids, the [:-1] drop and cyclic padding all agree
+
+
+def test_hpr_duplicates_and_padding_draws():
+    # class 17 stores 574 copies of point 0: exactly one representative of a duplicated visible point survives
+    cls = np.full(4, 17, np.int32)
+    _, ax, tr = _poses(4, 9)
+    P = S.transform_object_model(cases.ycb_models()[cls], ax, tr)
+    flipped, org = S.spherical_flip(P)
+    vis, num, flags = HPR.convexHull(torch.from_numpy(flipped).cuda(), torch.from_numpy(org).cuda(), return_flags=True)
+    flags = flags.cpu().numpy().astype(bool)
+    for k in range(4):
+        dup = np.where((P[k] == P[k, 0]).all(axis=1))[0]
+        assert flags[k, dup].sum() <= 1
+    # explicit padding draws pick floor(u * num_vis) among the visible ids
+    u = torch.rand(4, 2049, device="cuda")
+    vis2, num2 = HPR.convexHull(torch.from_numpy(flipped).cuda(), torch.from_numpy(org).cuda(), pad_uniform=u)
+    nv = int(num2[0])
+    ids = np.where(flags[0])[0][:-1]
+    r = nv + 5
+    want = P[0, ids[min(int(u[0, r].item() * nv), nv - 1)]]
+    assert (vis2[0, r].cpu().numpy() == want).all() and (vis2[0, :nv].cpu().numpy() == P[0, ids]).all()
+
+
+def test_fused_synthesizer_feeds_training():
+    from cloudaae_b200.train import CloudAAETrainer
+    b, n = 8, 256
+    syn = SegmentSynthesizer(load_models_xyz(), b, n, seed=3)
+    cls, ax, tr = _poses(b, 11)
+    c, a, t = torch.from_numpy(cls).cuda(), torch.from_numpy(ax).cuda(), torch.from_numpy(tr).cuda()
+    visible, target, noise = syn.synthesize(c, a, t)
+    torch.cuda.synchronize()
+    # every output row is one of the synthesized points; network input may contain occluder points
+    pts = syn.points.cpu().numpy()
+    for k in range(b):
+        allp = {tuple(p) for p in pts[k]}
+        assert all(tuple(p) in allp for p in visible[k].cpu().numpy())
+        objp = {tuple(p) for p in pts[k, :2048]}
+        assert all(tuple(p) in objp for p in target[k].cpu().numpy())
+    assert 0.5 * 0.004 / 3 < noise.std().item() < 1.5 * 0.004 / 3
+    v1 = visible.clone()
+    syn.synthesize(c, a, t)                       # new draws -> a different occluder -> (almost surely) different input
+    assert not torch.equal(v1, syn.visible)
+    tr_ = CloudAAETrainer(batch_size=b, num_point=n, seed=1)
+    l0 = tr_.train_step(syn.visible, syn.target, c, t, a, syn.noise).clone()
+    for _ in range(5):
+        syn.synthesize(c, a, t)
+        l = tr_.train_step(syn.visible, syn.target, c, t, a, syn.noise)
+    assert torch.isfinite(l).all() and l[0].item() < l0[0].item() * 1.5
