@@ -122,7 +122,7 @@ def ops_inputs(b: int, seed: int):
     return clouds, np.ascontiguousarray(pred, np.float32), np.ascontiguousarray(target, np.float32)
 
 
-def run_ours_ops(args, rank, world, local_rank):
+def run_ours_ops(args, rank, world, local_rank, with_cpu_baseline=True):
     import torch
     import torch.distributed as dist
 
@@ -259,41 +259,50 @@ def run_ours_ops(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": 3 * args.steps, "clocks": clocks, "wall_s_timed_region": t_wall,
     }
-    result["cpu_baseline"] = cpu_baseline_ops(sample_clouds=8)
+    if with_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline_ops(sample_clouds=8)
     return result
 
 
 
 # ----------------------------------------------------------------------------------------------
 # Workload "train": BASELINE.json configs[2]/[3] — the full train_cloudAAE_ycbv.py step at the repo
-# default batch (128 segments per GPU, num_point 256, k 10): input prep, get_model_dgcnn_mean_6d
-# forward, chamfer + pose losses, backward, (NCCL allreduce of the flat gradient), TF-style Adam.
+# default batch (128 segments per GPU, num_point 256, k 10): ON-LINE SYNTHESIS from pose records
+# (pose transform, spherical occluders, hidden point removal x2, visible-prefix selection, sensor
+# noise), input prep, get_model_dgcnn_mean_6d forward, chamfer + pose losses, backward,
+# (NCCL allreduce of the flat gradient), TF-style Adam.  One CUDA graph per step.
 TRAIN_B, TRAIN_N = 128, 256
+TRAIN_KEYS = ("class_id", "axisangle", "translation")
+TRAIN_METRIC = "train segments/sec"
 
 
-def train_inputs(b: int, seed: int, pool: int = 4):
-    """`pool` batches of b YCB-shaped segments (host arrays)."""
+def pose_batches(b: int, seed: int, pool: int = 8):
+    """`pool` batches of b pose records drawn uniformly from the committed fixture poses (host arrays)."""
     z = np.load(os.path.join(ROOT, "tests", "golden", "ycb_poses.npz"))
     out = []
     for i in range(pool):
-        rng = np.random.default_rng(seed * 1000 + i)
-        clouds = ycb_shaped_clouds(b, seed * 1000 + i)
-        sel = np.random.default_rng(seed * 1000 + i).integers(0, len(z["class_id"]), b)  # same draw as the clouds
-        out.append({
-            "visible": clouds, "target": np.ascontiguousarray(clouds[:, :4 * TRAIN_N]),
-            "class_id": z["class_id"][sel].astype(np.int32), "translation": z["translation"][sel].astype(np.float32),
-            "axisangle": z["axisangle"][sel].astype(np.float32),
-            "noise": (rng.standard_normal((b, TRAIN_N, 3)) * (0.004 / 3.0)).astype(np.float32)})
+        sel = np.random.default_rng(seed * 1000 + i).integers(0, len(z["class_id"]), b)
+        out.append({"class_id": z["class_id"][sel].astype(np.int32), "axisangle": z["axisangle"][sel].astype(np.float32),
+                    "translation": z["translation"][sel].astype(np.float32)})
     return out
 
 
-TRAIN_KEYS = ("visible", "target", "class_id", "translation", "axisangle", "noise")
+def train_config(world: int, extra=None):
+    cfg = {"workload": "train_cloudAAE_ycbv.py step, BASELINE.json configs[2]" + ("/[3]" if world > 1 else ""),
+           "global_batch": TRAIN_B * world, "batch_per_gpu": TRAIN_B, "num_point": TRAIN_N, "k_neighbor": 10,
+           "network": "get_model_dgcnn_mean_6d", "synthesis": "on-line, inside the timed step",
+           "parallelism": f"dp{world}: NCCL allreduce of the flat fp32 gradient, 2 buckets" if world > 1 else "single GPU"}
+    if extra:
+        cfg.update(extra)
+    return cfg
 
 
 def run_ours_train(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
+    from cloudaae_b200 import _capi
+    from cloudaae_b200.synthesis import SegmentSynthesizer, load_models_xyz
     from cloudaae_b200.train import CloudAAETrainer
 
     dev = torch.device("cuda", local_rank)
@@ -302,16 +311,17 @@ def run_ours_train(args, rank, world, local_rank):
     B = TRAIN_B
     pg = dist.group.WORLD if world > 1 else None
     tr = CloudAAETrainer(batch_size=B, num_point=TRAIN_N, device=dev, seed=0, process_group=pg)
-    pool_h = train_inputs(B, seed=rank)
+    syn = SegmentSynthesizer(load_models_xyz(device=dev), B, TRAIN_N, seed=1234 + rank)
+    pool_h = pose_batches(B, seed=rank)
     pool_d = [{k: torch.from_numpy(v).to(dev) for k, v in bt.items()} for bt in pool_h]
-    static = tr.capture(*[pool_d[0][k] for k in TRAIN_KEYS])
+    static = tr.capture_online(syn, *[pool_d[0][k] for k in TRAIN_KEYS])
 
-    def load(i):  # device-to-device refresh of the graph's static inputs (inputs already resident in HBM)
+    def load(i, src):  # refresh the graph's static pose records
         for dst, k in zip(static, TRAIN_KEYS):
-            dst.copy_(pool_d[i % len(pool_d)][k], non_blocking=True)
+            dst.copy_(src[i % len(src)][k], non_blocking=True)
 
     for i in range(args.warmup):
-        load(i); tr.replay()
+        load(i, pool_d); tr.replay()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if world > 1:
@@ -322,7 +332,7 @@ def run_ours_train(args, rank, world, local_rank):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for i in range(args.steps):
-        load(i); tr.replay()
+        load(i, pool_d); tr.replay()
     e.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -335,13 +345,12 @@ def run_ours_train(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     losses = tr.losses.cpu().tolist()
 
-    # e2e: host (pinned) batches -> H2D -> step -> D2H of the loss vector, every step
+    # ---- e2e: HOST pose records (pinned) -> H2D -> synthesis + step -> D2H of the loss vector, every step
     pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in bt.items()} for bt in pool_h]
     loss_h = torch.empty(4, dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
-        for dst, k in zip(static, TRAIN_KEYS):
-            dst.copy_(pinned[i % len(pinned)][k], non_blocking=True)
+        load(i, pinned)
         tr.replay()
         loss_h.copy_(tr.losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -361,30 +370,60 @@ def run_ours_train(args, rank, world, local_rank):
     h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
     if rank != 0:
         return None
-    ms = total_ms / args.steps
+
+    # ---- stage split and roofline of the dominant kernel (rank 0, after the timed region)
+    stream = torch.cuda.current_stream()
+
+    def timeit(fn, iters=20):
+        fn(); torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(iters):
+            fn()
+        b_.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / iters
+
+    c, ax, tl = static
+    t_syn = timeit(lambda: syn.synthesize(c, ax, tl))
     R = B * TRAIN_N
-    # dominant kernel: the dgcnn_agg contraction (fwd 2*R*320*1024, bwd twice that)
-    agg_flops = 3 * 2.0 * R * 320 * 1024
-    tens_peak = peaks["bf16_tflops_sustained"] / 2.0  # TF32 dense = half the measured bf16 rate
-    roofline = {"kernel": "dgcnn_agg GEMMs (fwd + dgrad + wgrad)", "bound": "tensor", "achieved": None,
-                "peak": tens_peak, "unit": "TFLOP/s", "frac": None, "traffic": None, "peak_source": peaks["source"],
-                "algorithmic_flops_per_step": agg_flops,
-                "note": "filled from per-kernel timing once measured; see profiles/"}
+    eng, lib, st = tr.engine, _capi.lib(), stream.cuda_stream
+    W = tr.v["dgcnn_agg/weights"]
+
+    def agg(ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc):
+        _capi.check(lib.caae_gemm_tf32(ta, tb, M, N, K, A.data_ptr(), lda, Bm.data_ptr(), ldb, C.data_ptr(), ldc, None, 0, st), "gemm")
+
+    scratch = torch.empty(R, 1024, device=dev)
+    dwt = torch.empty(320, 1024, device=dev)
+    t_fwd = timeit(lambda: agg(0, 0, R, 1024, 320, eng.hcat, 320, W, 1024, scratch, 1024))
+    t_dgrad = timeit(lambda: agg(0, 1, R, 320, 1024, scratch, 1024, W, 1024, eng.d_hcat, 320))
+    t_wgrad = timeit(lambda: agg(1, 0, 320, 1024, R, eng.hcat, 320, scratch, 1024, dwt, 1024))
+    flops = 2.0 * R * 320 * 1024
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0  # TF32 dense = half the measured bf16 rate
+    gemms = {"dgcnn_agg_fwd": t_fwd, "dgcnn_agg_dgrad": t_dgrad, "dgcnn_agg_wgrad": t_wgrad}
+    dom = max(gemms, key=gemms.get)
+    achieved = flops / (gemms[dom] * 1e-3) / 1e12
+    roofline = {"kernel": f"gemm_tf32_kernel ({dom}: 32768 x 1024 x 320, tcgen05 TF32)", "bound": "tensor",
+                "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+                "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained / 2)",
+                "algorithmic_flops_per_launch": flops, "ms_per_launch": gemms[dom],
+                "all_agg_gemms_ms": gemms}
+    ms = total_ms / args.steps
     return {
-        "metric": "train segments/sec", "value": B * world / (ms * 1e-3), "unit": "segments/s", "n_gpus": world,
+        "metric": TRAIN_METRIC, "value": B * world / (ms * 1e-3), "unit": "segments/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (committed YCB model fixture x fixture poses, random init weights)",
-        "config": {"workload": "train_cloudAAE_ycbv.py step, BASELINE.json configs[2]" + ("/[3]" if world > 1 else ""),
-                   "global_batch": B * world, "batch_per_gpu": B, "num_point": TRAIN_N, "k_neighbor": 10,
-                   "model": "get_model_dgcnn_mean_6d", "synthesis": "pose transform only (GPU HPR not in the timed region yet)",
-                   "l2": "per-step working set (~0.4 GB of activations) exceeds the 126 MB L2; no flush",
-                   "parallelism": f"dp{world}: one NCCL allreduce of the flat fp32 gradient" if world > 1 else "single GPU",
-                   "cuda_graph": True},
-        "roofline": roofline, "losses_last_step": losses,
+        "vs_baseline": None, "dtype": "f32 (dgcnn_agg contractions: tf32 multiply, f32 accumulate)",
+        "data": "synthetic: committed YCB model fixture x fixture pose records, Philox occluders/noise, random-init weights",
+        "config": train_config(world, {"cuda_graph": True,
+                                       "l2": "per-step working set (~0.5 GB of activations) exceeds the 126 MB L2; no flush"}),
+        "roofline": roofline,
+        "stage_ms": {"synthesis": t_syn, "train_step_total": ms},
+        "losses_last_step": losses,
         "e2e": {"value": B * world / (e2e_s / args.steps), "unit": "segments/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 16},
-        "gpu_launches": None, "clocks": clocks,
+        "gpu_launches": int(tr.launches_per_step) * args.steps, "clocks": clocks,
     }
+
 
 # ----------------------------------------------------------------------------------------------
 def _ref_ops_pass(clouds, pred, target, threads):
@@ -461,6 +500,129 @@ def run_reference_ops(args):
 
 
 # ----------------------------------------------------------------------------------------------
+def _ref_train_setup(b):
+    import torch
+
+    from oracle import model_ref as MR
+    params = {k: v.requires_grad_(not k.endswith(("ema_mean", "ema_var")))
+              for k, v in MR.init_params(MR.DGCNN_LAYERS, seed=0, perturb=False).items()}
+    names = [k for k in params if params[k].requires_grad]
+    m = {k: torch.zeros_like(params[k]) for k in names}
+    v = {k: torch.zeros_like(params[k]) for k in names}
+    return params, names, m, v
+
+
+def _synth_one(args):
+    """Per-sample synthesis exactly as the reference's tf.data map chain (one sample per call)."""
+    from oracle import synthesis as S
+    model, ax, tr, seed = args
+    rng = np.random.default_rng(seed)
+    P = S.transform_object_model(model[None], ax[None], tr[None])
+    occ = S.spherical_occluder(tr[None, 2], rng.standard_normal((1, 2, 3)), rng.standard_normal((1, 2, 200, 3)))
+    fl, org = S.spherical_flip(np.concatenate([P, occ], 1))
+    vis, _, _ = S.convex_hull_visible(fl, org)
+    fl2, org2 = S.spherical_flip(P)
+    vis2, _, _ = S.convex_hull_visible(fl2, org2)
+    return vis[0, :TRAIN_N], vis2[0, :4 * TRAIN_N]
+
+
+def run_reference_train(args):
+    """--impl reference: the reference's CPU path for the same step on this box's host cores —
+    NumPy + scipy.spatial.ConvexHull synthesis (the reference's own library call) in a process pool,
+    the literal TF graph restated in torch-CPU fp32 (all threads), chamfer through the reference's
+    own CPU NnDistance/NnDistanceGrad OpKernels when oracle/_ref is built, TF-formula Adam.
+    Each step is a bounded SAMPLE of the 128-segment batch."""
+    import multiprocessing as mp
+
+    import torch
+
+    from oracle import model_ref as MR
+    from oracle import ops as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = 16  # bounded sample per step (the full 128-segment step takes ~15 s on 8 cores)
+    models = np.load(os.path.join(ROOT, "tests", "golden", "ycb_models_xyz.npy"))
+    params, names, m, v = _ref_train_setup(b)
+    use_ref = O.have_ref()
+
+    class Chamfer(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, pred, label):
+            fn = O.ref_cpu_nn_distance if use_ref else (lambda x, y: O.nn_distance(x, y, "cpu", threads=cores))
+            d1, i1, d2, i2 = fn(pred.detach().numpy(), label.numpy())
+            ctx.save = (pred.detach().numpy(), label.numpy(), i1, i2)
+            return torch.from_numpy(d1), torch.from_numpy(d2)
+
+        @staticmethod
+        def backward(ctx, g1, g2):
+            x1, x2, i1, i2 = ctx.save
+            fn = O.ref_cpu_nn_distance_grad if use_ref else O.nn_distance_grad
+            gx1, _ = fn(x1, x2, g1.numpy(), i1, g2.numpy(), i2)
+            return torch.from_numpy(gx1), None
+
+    pool = mp.get_context("fork").Pool(cores)
+    batches = pose_batches(b, seed=0)
+
+    def step(i, t_idx):
+        bt = batches[i % len(batches)]
+        jobs = [(models[bt["class_id"][k]], bt["axisangle"][k], bt["translation"][k], 1000 * i + k) for k in range(b)]
+        res = pool.map(_synth_one, jobs)
+        vis = torch.from_numpy(np.stack([r[0] for r in res])); tgt = torch.from_numpy(np.stack([r[1] for r in res]))
+        noise = torch.randn(b, TRAIN_N, 3) * (0.004 / 3.0)
+        x, mean = MR.prepare_input(vis, torch.from_numpy(bt["class_id"]), noise, num_point=TRAIN_N)
+        recon, rot, trans_res, _ = MR.get_model_dgcnn_mean_6d(x, params, True, True, 10, MR.bn_decay_schedule(t_idx, b))
+        d1, d2 = Chamfer.apply(recon + mean.unsqueeze(1), tgt)
+        chamfer = (d1 + d2).mean()
+        tl, _ = MR.get_translation_error(trans_res + mean, torch.from_numpy(bt["translation"]))
+        rl, _ = MR.get_rotation_error(rot.double(), torch.from_numpy(bt["axisangle"]).double())
+        total = 1000 * chamfer + 10 * tl + rl.float()
+        for k in names:
+            params[k].grad = None
+        total.backward()
+        with torch.no_grad():
+            for k in names:
+                g = params[k].grad if params[k].grad is not None else torch.zeros_like(params[k])
+                p_new, m[k], v[k] = MR.adam_step(params[k], g, m[k], v[k], t_idx + 1)
+                params[k].copy_(p_new)
+        return float(total.item())
+
+    t_idx = 0
+    for i in range(max(1, min(args.warmup, 2))):
+        step(i, t_idx); t_idx += 1
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, t_idx); t_idx += 1
+    dt = time.perf_counter() - t0
+    pool.close()
+    value = b * args.steps / dt
+    kind = "port"  # TensorFlow 1.12 is not installable here; only the chamfer op is the reference's own binary
+    sample = (f"{args.steps} steps x {b}-segment sample of the {TRAIN_B}-segment step: scipy-Qhull synthesis in a "
+              f"{cores}-process pool, torch-CPU fp32 restatement of the TF graph on {cores} threads, chamfer via "
+              f"{'the reference CPU OpKernels (oracle/_ref)' if use_ref else 'the oracle port'}, Adam")
+    return {
+        "impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": "segments/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same fixtures as the GPU arm)",
+        "config": train_config(1, {"reference_sample_per_step": b}),
+        "cpu_baseline": {"value": value, "unit": "segments/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def cpu_baseline_train(seconds: float = 12.0):
+    """cpu_baseline leg of the default run: the same reference step, run for ~`seconds` s on rank 0."""
+    class A:  # minimal args
+        gpus, warmup = 1, 1
+        steps = 3
+    t0 = time.perf_counter()
+    res = run_reference_train(A)
+    res["cpu_baseline"]["wall_s"] = time.perf_counter() - t0
+    return res["cpu_baseline"]
+
+
+# ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -477,7 +639,8 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(run_reference_ops(args)), flush=True)  # TODO(train): reference arm of the train step
+            fn = run_reference_train if args.workload in ("auto", "train") else run_reference_ops
+            print(json.dumps(fn(args)), flush=True)
         return 0
 
     import torch
@@ -491,6 +654,15 @@ def main():
     try:
         if args.workload in ("auto", "train"):
             result = run_ours_train(args, rank, world, local_rank)
+            if rank == 0:
+                # the metric also asks for FPS / nn_distance achieved GB/s: run the tf_ops microbench
+                # (BASELINE configs[1]) on rank 0 after the timed region and attach its kernel table
+                class OpsArgs:
+                    steps, warmup = 30, 3
+                ops = run_ours_ops(OpsArgs, 0, 1, local_rank, with_cpu_baseline=False)
+                result["ops_microbench"] = {"segments_per_s": ops["value"], "ms_per_pass": ops["ms_per_step"],
+                                            "kernels": ops["kernels"], "config": ops["config"]}
+                result["cpu_baseline"] = cpu_baseline_train()
         else:
             result = run_ours_ops(args, rank, world, local_rank)
         if rank == 0:

@@ -112,7 +112,11 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+COUNTER = [0]  # C-ABI kernel-launching calls issued by this process (each launches >= 1 kernel)
+
+
 def check(status: int, what: str) -> None:
+    COUNTER[0] += 1
     if status != 0:
         msg = lib().caae_status_string(status).decode()
         raise CloudAAENativeError(f"{what} failed with status {status}: {msg}")

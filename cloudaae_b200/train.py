@@ -58,6 +58,7 @@ class CloudAAETrainer:
         self.losses = torch.zeros(4, **f32)  # total, chamfer, trans, rot
         self._graph = None
         self._static = None
+        self.launches_per_step = 0
         # gradient exchange: bucket 1 = everything after the encoder (FC decoder + pose heads), complete
         # as soon as the FC backward has run; bucket 0 = the encoder, complete at the end of backward.
         enc_last = "dgcnn_agg" if model == "dgcnn" else "pn_conv5_encoder"
@@ -119,26 +120,44 @@ class CloudAAETrainer:
         self.apply_gradients()
         return self.losses
 
+    # ------------------------------------------------------------------ on-line synthesis
+    def train_step_online(self, synthesizer, class_id, axisangle, translation):
+        """train_cloudAAE_ycbv.py's full step: pose records -> on-line synthesis (pose transform, occluder,
+        hidden point removal, visible-prefix selection, sensor noise) -> train_step."""
+        visible, target, noise = synthesizer.synthesize(class_id, axisangle, translation)
+        return self.train_step(visible, target, class_id, translation, axisangle, noise)
+
     # ------------------------------------------------------------------ CUDA graph
-    def capture(self, visible, target, class_id, translation, axisangle, noise=None, warmup: int = 2):
-        """Capture train_step on static input buffers; afterwards `replay()` runs one step per call
-        on whatever those buffers hold.  Optimiser/BN state advances exactly as in eager mode."""
-        self._static = tuple(t.clone() if t is not None else None
-                             for t in (visible, target, class_id, translation, axisangle, noise))
+    def _capture(self, fn, static, warmup):
         snap = (self.v.flat.clone(), self.v.ema.clone(), self.adam_m.clone(), self.adam_v.clone(), self.state.clone())
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self.train_step(*self._static)
+                fn(*static)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         self._graph = torch.cuda.CUDAGraph()
+        before = _capi.COUNTER[0]
         with torch.cuda.graph(self._graph):
-            self.train_step(*self._static)
+            fn(*static)
+        self.launches_per_step = _capi.COUNTER[0] - before  # C-ABI launches captured into one step
         # warm-up and capture must not count as training steps
         for dst, src in zip((self.v.flat, self.v.ema, self.adam_m, self.adam_v, self.state), snap):
             dst.copy_(src)
-        return self._static
+        self._static = static
+        return static
+
+    def capture(self, visible, target, class_id, translation, axisangle, noise=None, warmup: int = 2):
+        """Capture train_step on static input buffers; afterwards `replay()` runs one step per call
+        on whatever those buffers hold.  Optimiser/BN state advances exactly as in eager mode."""
+        static = tuple(t.clone() if t is not None else None
+                       for t in (visible, target, class_id, translation, axisangle, noise))
+        return self._capture(self.train_step, static, warmup)
+
+    def capture_online(self, synthesizer, class_id, axisangle, translation, warmup: int = 2):
+        """Capture synthesis + train_step in ONE graph; static inputs are the pose records only."""
+        static = (class_id.clone(), axisangle.clone(), translation.clone())
+        return self._capture(lambda c, a, t: self.train_step_online(synthesizer, c, a, t), static, warmup)
 
     def replay(self):
         self._graph.replay()
