@@ -20,7 +20,8 @@
 // solved per point by Seidel's incremental algorithm: keep the current optimum; a violated
 // constraint moves it to the minimum-norm point of that constraint's boundary line clipped by all
 // constraints seen before; an empty clip interval proves the point hidden.  Constraints are visited
-// near-to-far through a 16x16 grid over (u,v) so re-solves happen while "seen before" is tiny.
+// neighbourhood-first through a 32x32 grid over (u,v) (so re-solves happen while "seen before" is
+// ~100 points), then every remaining point as the global verification.
 // fp64 predicates on the fp32 flipped coordinates; measured against Qhull on the reference's own
 // fixtures the visible sets are identical (tests/test_gpu_synthesis.py reports the IoU).
 //
@@ -30,26 +31,9 @@
 namespace caae {
 
 constexpr int SY_THREADS = 1024;
-constexpr int SY_G = 16;                 // grid cells per axis over the (u,v) bounding box
-constexpr int SY_NOFF = (2 * SY_G - 1) * (2 * SY_G - 1);
+constexpr int SY_G = 32;                 // grid cells per axis over the (u,v) bounding box (one cell per thread)
 constexpr int SY_MAXN = 4096;            // points per cloud the HPR kernel supports
-
-struct OffTable { signed char dx[SY_NOFF], dy[SY_NOFF]; };
-
-// cell offsets sorted by Chebyshev ring (near-to-far), built at compile time
-constexpr OffTable make_off_table() {
-  OffTable t{};
-  int m = 0;
-  for (int r = 0; r < SY_G; ++r)
-    for (int y = -r; y <= r; ++y)
-      for (int x = -r; x <= r; ++x) {
-        const int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y;
-        if ((ax > ay ? ax : ay) != r) continue;
-        t.dx[m] = (signed char)x; t.dy[m] = (signed char)y; ++m;
-      }
-  return t;
-}
-__constant__ OffTable c_off = make_off_table();
+constexpr int SY_LOCAL = 9;              // phase 1 visits the 3x3 cell neighbourhood
 
 // ---- Philox4x32-10 -----------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
@@ -189,43 +173,133 @@ synth_points_kernel(int nm, int no, const float* __restrict__ models, const int*
 }
 
 // ---- hidden point removal + visible-prefix selection ---------------------------------------------
-struct HprCtx {
-  const double* U; const double* V; const double* W;
-  const unsigned short* order; const int* cell_start;
-  double ui, vi, wi, kappa;
-  int i, cx, cy;
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, m); hi = __shfl_xor_sync(0xffffffffu, hi, m);
+  return __hiloint2double(hi, lo);
+}
+
+// Everything the per-point LP needs, in shared memory.
+struct HprShared {
+  const double *U, *V, *W;          // lifted coordinates (paraboloid-shifted), fp64
+  const unsigned short* order;      // point ids sorted by grid cell
+  const unsigned char *cellx, *celly;
+  const int* cell_start;            // [SY_G*SY_G + 1]
+  double kappa;
+  int n;
 };
 
-// Minimum-norm point of the boundary line of constraint (du,dv,rhs) clipped by every constraint
-// visited before position (o_end, k_end).  Returns false when the clip interval is empty.
-__device__ bool hpr_resolve(const HprCtx& c, double du, double dv, double rhs, int o_end, int k_end, double& sa,
-                            double& sb) {
+// The constraint sequence of point i is: its 3x3 cell neighbourhood (9 cell segments of `order`),
+// then every point OUTSIDE that neighbourhood in index order.  Nbhd caches the 9 segments.
+struct Nbhd {
+  int* start;  // [SY_LOCAL]      per-warp shared-memory scratch
+  int* pre;    // [SY_LOCAL + 1]  exclusive prefix of the segment lengths
+  int cx, cy;
+};
+__device__ __forceinline__ void make_nbhd(const HprShared& h, int i, int* scratch, Nbhd& nb) {
+  nb.start = scratch; nb.pre = scratch + SY_LOCAL;
+  nb.cx = h.cellx[i]; nb.cy = h.celly[i];
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    int run = 0;
+    nb.pre[0] = 0;
+    for (int o = 0; o < SY_LOCAL; ++o) {
+      const int x = nb.cx + (o % 3) - 1, y = nb.cy + (o / 3) - 1;
+      const bool valid = x >= 0 && x < SY_G && y >= 0 && y < SY_G;
+      const int cell = valid ? y * SY_G + x : 0;
+      nb.start[o] = valid ? h.cell_start[cell] : 0;
+      run += valid ? h.cell_start[cell + 1] - h.cell_start[cell] : 0;
+      nb.pre[o + 1] = run;
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ int nbhd_elem(const HprShared& h, const Nbhd& nb, int e) {
+  int o = 0;
+#pragma unroll
+  for (int q = 1; q < SY_LOCAL; ++q) o += (e >= nb.pre[q]) ? 1 : 0;
+  return h.order[nb.start[o] + (e - nb.pre[o])];
+}
+__device__ __forceinline__ bool in_nbhd(const HprShared& h, const Nbhd& nb, int j) {
+  return abs((int)h.cellx[j] - nb.cx) <= 1 && abs((int)h.celly[j] - nb.cy) <= 1;
+}
+
+// Warp-cooperative clip: minimum-norm point of the boundary line of constraint (du,dv,rhs) of point i,
+// subject to the first `e_end` neighbourhood constraints and the non-neighbourhood points of index
+// < j_end.  All arguments are warp-uniform; all lanes return the same result.
+__device__ bool hpr_clip_warp(const HprShared& h, const Nbhd& nb, int i, double ui, double vi, double wi, double du,
+                              double dv, double rhs, int e_end, int j_end, double& sa, double& sb) {
+  const int lane = threadIdx.x & 31;
   const double r2 = du * du + dv * dv;
   const double p0a = du * rhs / r2, p0b = dv * rhs / r2, da = -dv, db = du;
   double lo = -INFINITY, hi = INFINITY;
-  for (int o = 0; o <= o_end; ++o) {
-    const int x = c.cx + c_off.dx[o], y = c.cy + c_off.dy[o];
-    if (x < 0 || x >= SY_G || y < 0 || y >= SY_G) continue;
-    const int cell = y * SY_G + x;
-    const int k1 = (o == o_end) ? k_end : c.cell_start[cell + 1];
-    for (int k = c.cell_start[cell]; k < k1; ++k) {
-      const int j = c.order[k];
-      if (j == c.i) continue;
-      const double eu = c.U[j] - c.ui, ev = c.V[j] - c.vi;
-      const double s2 = eu * eu + ev * ev;
-      if (s2 == 0.0) continue;
-      const double rk = (c.W[j] - c.wi) - 0.5 * c.kappa * s2;
-      const double den = da * eu + db * ev, num = rk - (p0a * eu + p0b * ev);
-      if (den > 0.0) lo = fmax(lo, num / den);
-      else if (den < 0.0) hi = fmin(hi, num / den);
-      else if (num > 0.0) return false;
-    }
+  auto clip = [&](int j) {
+    const double eu = h.U[j] - ui, ev = h.V[j] - vi;
+    const double s2 = eu * eu + ev * ev;
+    if (s2 == 0.0) return;
+    const double rk = (h.W[j] - wi) - 0.5 * h.kappa * s2;
+    const double den = da * eu + db * ev, num = rk - (p0a * eu + p0b * ev);
+    if (den > 0.0) lo = fmax(lo, num / den);
+    else if (den < 0.0) hi = fmin(hi, num / den);
+    else if (num > 0.0) lo = INFINITY;
+  };
+  for (int e = lane; e < e_end; e += 32) {
+    const int j = nbhd_elem(h, nb, e);
+    if (j != i) clip(j);
   }
+  for (int j = lane; j < j_end; j += 32)
+    if (!in_nbhd(h, nb, j)) clip(j);
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) { lo = fmax(lo, shfl_xor_d(lo, m)); hi = fmin(hi, shfl_xor_d(hi, m)); }
   if (lo > hi) return false;
   const double t = fmin(fmax(0.0, lo), hi);
   sa = p0a + t * da; sb = p0b + t * db;
   return true;
 }
+
+// One warp runs the incremental LP of point i over elements [e_from, m) of its neighbourhood and then
+// (when j_to > 0) over the non-neighbourhood points [0, j_to).  32 constraints are tested per step; the
+// first violated one (in sequence order) triggers a cooperative clip and the scan resumes right after
+// it.  Returns false when the point is proven hidden; (sa, sb) is the running optimum.
+__device__ bool hpr_lp_warp(const HprShared& h, const Nbhd& nb, int i, int j_to, double& sa, double& sb) {
+  const int lane = threadIdx.x & 31;
+  const double ui = h.U[i], vi = h.V[i], wi = h.W[i];
+  const int m = nb.pre[SY_LOCAL];
+  // pos runs over the concatenated sequence: [0, m) neighbourhood elements, [m, m + j_to) = index j = pos - m
+  const int total = m + j_to;
+  int pos = 0;
+  while (pos < total) {
+    const int q = pos + lane;
+    int j = -1;
+    if (q < m) j = nbhd_elem(h, nb, q);
+    else if (q < total) { j = q - m; if (in_nbhd(h, nb, j)) j = -1; }
+    bool viol = false, hidden = false;
+    double du = 0.0, dv = 0.0, rhs = 0.0;
+    if (j >= 0 && j != i) {
+      du = h.U[j] - ui; dv = h.V[j] - vi;
+      const double r2 = du * du + dv * dv;
+      const double dw = h.W[j] - wi;
+      if (r2 == 0.0) hidden = dw > 0.0 || (dw == 0.0 && j < i);   // same direction: nearer / lower index stays
+      else { rhs = dw - 0.5 * h.kappa * r2; viol = rhs - (sa * du + sb * dv) > 0.0; }
+    }
+    const unsigned mv = __ballot_sync(0xffffffffu, viol), mh = __ballot_sync(0xffffffffu, hidden);
+    const int fv = mv ? __ffs(mv) - 1 : 32, fh = mh ? __ffs(mh) - 1 : 32;
+    if (fh < fv) return false;                 // a "hidden" verdict earlier in the sequence than any violation
+    if (fv == 32) { pos += 32; continue; }
+    du = shfl_d(du, fv); dv = shfl_d(dv, fv); rhs = shfl_d(rhs, fv);
+    const int qv = pos + fv;                   // sequence position of the violated constraint
+    if (!hpr_clip_warp(h, nb, i, ui, vi, wi, du, dv, rhs, min(qv, m), max(qv - m, 0), sa, sb)) return false;
+    pos = qv + 1;
+  }
+  return true;
+}
+
+constexpr int SY_SLICE = 256;  // phase-2 verification: points per (survivor, slice) work item
 
 __global__ void __launch_bounds__(SY_THREADS)
 hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restrict__ org, int org_stride_pts, int take,
@@ -235,16 +309,23 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
   double* U = reinterpret_cast<double*>(sy_smem);
   double* V = U + n;
   double* W = V + n;
-  unsigned short* order = reinterpret_cast<unsigned short*>(W + n);
-  unsigned char* cellid = reinterpret_cast<unsigned char*>(order + n);
-  unsigned char* flag = cellid + n;
-  int* ids = reinterpret_cast<int*>(sy_smem);  // reuses the U region after the LP phase
-  __shared__ int cell_start[SY_G * SY_G + 1];
-  __shared__ int cell_fill[SY_G * SY_G];
+  double* SA = W + n;                                          // survivors' optima after phase 1
+  double* SB = SA + n;
+  float4* F4 = reinterpret_cast<float4*>(SB + n);              // fp32 copy (u, v, w - w_ref, 0) for the phase-2 filter
+  unsigned short* order = reinterpret_cast<unsigned short*>(F4 + n);
+  unsigned short* surv = order + n;
+  unsigned char* cellx = reinterpret_cast<unsigned char*>(surv + n);
+  unsigned char* celly = cellx + n;
+  unsigned char* flag = celly + n;
+  unsigned char* dirty = flag + n;
+  int* cell_start = reinterpret_cast<int*>(dirty + ((n + 3) & ~3));   // [SY_G*SY_G + 1]
+  int* cell_fill = cell_start + SY_G * SY_G + 1;                       // [SY_G*SY_G]
+  int* ids = reinterpret_cast<int*>(sy_smem);  // reuses the U region after the LP phases
   __shared__ float s_redf[32];
   __shared__ int s_warp_tot[32];
   __shared__ float s_box[4];
-  __shared__ int s_count;
+  __shared__ int s_count, s_queue;
+  __shared__ int s_nb[SY_THREADS / 32][2 * SY_LOCAL + 2];
 
   const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* __restrict__ f = flipped + (size_t)cloud * n * 3;
@@ -262,13 +343,18 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
     const double x = (double)f[i * 3 + 0], y = (double)f[i * 3 + 1], z = (double)f[i * 3 + 2];
     const double u = x / z, v = y / z;
     U[i] = u; V[i] = v;
-    W[i] = -rho * rho / z + 0.5 * rho * (u * u + v * v);  // paraboloid-shifted lift
+    const double w = -rho * rho / z + 0.5 * rho * (u * u + v * v);  // paraboloid-shifted lift
+    W[i] = w;
+    F4[i] = make_float4((float)u, (float)v, (float)(w + rho), 0.f);  // w ~ -rho: recentre before rounding to fp32
     umin = fminf(umin, (float)u); umax = fmaxf(umax, (float)u);
     vmin = fminf(vmin, (float)v); vmax = fmaxf(vmax, (float)v);
   }
   umax = block_max(umax, s_redf); vmax = block_max(vmax, s_redf);
   umin = -block_max(-umin, s_redf); vmin = -block_max(-vmin, s_redf);
-  if (tid == 0) { s_box[0] = umin; s_box[1] = vmin; s_box[2] = fmaxf(umax - umin, 1e-30f); s_box[3] = fmaxf(vmax - vmin, 1e-30f); }
+  if (tid == 0) {
+    s_box[0] = umin; s_box[1] = vmin; s_box[2] = fmaxf(umax - umin, 1e-30f); s_box[3] = fmaxf(vmax - vmin, 1e-30f);
+    s_count = 0; s_queue = 0;
+  }
   for (int c = tid; c < SY_G * SY_G; c += SY_THREADS) cell_fill[c] = 0;
   __syncthreads();
 
@@ -276,58 +362,109 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
   for (int i = tid; i < n; i += SY_THREADS) {
     int cx = (int)(((float)U[i] - s_box[0]) / s_box[2] * SY_G), cy = (int)(((float)V[i] - s_box[1]) / s_box[3] * SY_G);
     cx = min(max(cx, 0), SY_G - 1); cy = min(max(cy, 0), SY_G - 1);
-    cellid[i] = (unsigned char)(cy * SY_G + cx);
+    cellx[i] = (unsigned char)cx; celly[i] = (unsigned char)cy;
+    flag[i] = 0; dirty[i] = 0;
     atomicAdd(&cell_fill[cy * SY_G + cx], 1);
   }
   __syncthreads();
-  if (warp == 0) {  // exclusive scan of 256 counts by one warp (8 per lane)
-    int loc[8], sum = 0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { loc[e] = cell_fill[lane * 8 + e]; sum += loc[e]; }
-    int inc = sum;
+  {  // exclusive scan of SY_G*SY_G (= SY_THREADS) counts, one per thread
+    static_assert(SY_G * SY_G == SY_THREADS, "one cell per thread");
+    const int v = cell_fill[tid];
+    int inc = v;
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    int run = inc - sum;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { cell_start[lane * 8 + e] = run; run += loc[e]; }
-    if (lane == 31) cell_start[SY_G * SY_G] = run;
+    if (lane == 31) s_warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = s_warp_tot[lane];
+      int iw = w;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iw, o); if (lane >= o) iw += t; }
+      s_warp_tot[lane] = iw - w;
+    }
+    __syncthreads();
+    const int excl = s_warp_tot[warp] + inc - v;
+    cell_start[tid] = excl;
+    if (tid == SY_THREADS - 1) cell_start[SY_G * SY_G] = excl + v;
+    cell_fill[tid] = excl;
   }
   __syncthreads();
-  for (int c = tid; c < SY_G * SY_G; c += SY_THREADS) cell_fill[c] = cell_start[c];
-  __syncthreads();
-  for (int i = tid; i < n; i += SY_THREADS) order[atomicAdd(&cell_fill[cellid[i]], 1)] = (unsigned short)i;
+  for (int i = tid; i < n; i += SY_THREADS) order[atomicAdd(&cell_fill[celly[i] * SY_G + cellx[i]], 1)] = (unsigned short)i;
   __syncthreads();
 
-  // ---- per-point incremental LP, points taken in cell order so a warp walks the same cells
-  HprCtx c;
-  c.U = U; c.V = V; c.W = W; c.order = order; c.cell_start = cell_start; c.kappa = rho;
-  for (int t = tid; t < n; t += SY_THREADS) {
+  HprShared h;
+  h.U = U; h.V = V; h.W = W; h.order = order; h.cellx = cellx; h.celly = celly; h.cell_start = cell_start;
+  h.kappa = rho; h.n = n;
+
+  // ---- phase 1: one WARP per point (dynamic queue, cell order): incremental LP over the point's 3x3
+  // cell neighbourhood, where nearly all re-solves happen.  Survivors (~45 %) are queued with their optimum.
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&s_queue, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= n) break;
     const int i = order[t];
-    c.i = i; c.ui = U[i]; c.vi = V[i]; c.wi = W[i];
-    c.cx = cellid[i] % SY_G; c.cy = cellid[i] / SY_G;
+    Nbhd nb;
+    make_nbhd(h, i, s_nb[warp], nb);
     double sa = 0.0, sb = 0.0;
-    bool vis = true;
-    for (int o = 0; o < SY_NOFF && vis; ++o) {
-      const int x = c.cx + c_off.dx[o], y = c.cy + c_off.dy[o];
-      if (x < 0 || x >= SY_G || y < 0 || y >= SY_G) continue;
-      const int cell = y * SY_G + x;
-      const int k1 = cell_start[cell + 1];
-      for (int k = cell_start[cell]; k < k1; ++k) {
-        const int j = order[k];
-        if (j == i) continue;
-        const double du = U[j] - c.ui, dv = V[j] - c.vi;
-        const double r2 = du * du + dv * dv;
-        const double dw = W[j] - c.wi;
-        if (r2 == 0.0) {  // same direction: the nearer one (or, for duplicates, the lower index) stays
-          if (dw > 0.0 || (dw == 0.0 && j < i)) { vis = false; break; }
-          continue;
-        }
-        const double rhs = dw - 0.5 * c.kappa * r2;
-        if (rhs - (sa * du + sb * dv) > 0.0) {
-          if (!hpr_resolve(c, du, dv, rhs, o, k, sa, sb)) { vis = false; break; }
-        }
-      }
+    if (hpr_lp_warp(h, nb, i, 0, sa, sb) && lane == 0) {
+      const int slot = atomicAdd(&s_count, 1);
+      surv[slot] = (unsigned short)i; SA[slot] = sa; SB[slot] = sb;
     }
-    flag[i] = vis ? 1 : 0;
+  }
+  __syncthreads();
+
+  // ---- phase 2: verify every survivor's optimum against all points, as (survivor, 256-point slice)
+  // work items.  Lanes of a warp share the slice (broadcast LDS.128 of the fp32 copy); a conservative
+  // fp32 evaluation dismisses constraints that are clearly slack, the few within `tol` of tight are
+  // re-evaluated in fp64; a genuine violation marks the survivor dirty for phase 3.
+  const int nsurv = s_count;
+  const int spad = (nsurv + 31) & ~31;
+  const int nslice = (n + SY_SLICE - 1) / SY_SLICE;
+  const float kh = 0.5f * (float)rho;
+  for (int q = tid; q < spad * nslice; q += SY_THREADS) {
+    const int sl = q / spad, sidx = q - sl * spad;
+    if (sidx >= nsurv) continue;
+    const int i = surv[sidx];
+    if (dirty[i]) continue;
+    const float4 fi = F4[i];
+    const double sa = SA[sidx], sb = SB[sidx];
+    const float saf = (float)sa, sbf = (float)sb;
+    const int cx = cellx[i], cy = celly[i];
+    const int j1 = min(n, (sl + 1) * SY_SLICE);
+    bool bad = false;
+    for (int j = sl * SY_SLICE; j < j1; ++j) {
+      const float4 fj = F4[j];
+      const float duf = fj.x - fi.x, dvf = fj.y - fi.y;
+      const float r2f = fmaf(duf, duf, dvf * dvf);
+      const float rhsf = (fj.z - fi.z) - kh * r2f;
+      const float dotf = fmaf(saf, duf, sbf * dvf);
+      const float tol = 1e-3f + 2e-5f * (fabsf(rhsf) + fabsf(dotf) + kh * r2f);
+      if (rhsf - dotf <= -tol) continue;                                  // clearly slack
+      if (abs((int)cellx[j] - cx) <= 1 && abs((int)celly[j] - cy) <= 1) continue;  // handled in phase 1
+      const double du = U[j] - U[i], dv = V[j] - V[i];
+      const double r2 = du * du + dv * dv, dw = W[j] - W[i];
+      if (r2 == 0.0) { if (dw > 0.0 || (dw == 0.0 && j < i)) bad = true; continue; }
+      if ((dw - 0.5 * rho * r2) - (sa * du + sb * dv) > 0.0) bad = true;
+    }
+    if (bad) dirty[i] = 1;
+  }
+  __syncthreads();
+
+  // ---- phase 3: the rare dirty survivors redo the LP over the full sequence (neighbourhood, then all
+  // other points in index order), one warp each; clean survivors are visible.
+  if (tid == 0) s_queue = 0;
+  __syncthreads();
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&s_queue, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= nsurv) break;
+    const int i = surv[t];
+    if (!dirty[i]) { if (lane == 0) flag[i] = 1; continue; }
+    Nbhd nb;
+    make_nbhd(h, i, s_nb[warp], nb);
+    double sa = 0.0, sb = 0.0;
+    const bool vis = hpr_lp_warp(h, nb, i, n, sa, sb);
+    if (lane == 0) flag[i] = vis ? 1 : 0;
   }
   __syncthreads();
 
@@ -339,7 +476,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
   int inc = cnt;
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
   if (lane == 31) s_warp_tot[warp] = inc;
-  __syncthreads();  // every thread is past the LP phase: the U region may now be reused for ids[]
+  __syncthreads();  // every thread is past the LP phases: the U region may now be reused for ids[]
   if (warp == 0) {
     int v = s_warp_tot[lane], iv = v;
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
@@ -407,7 +544,8 @@ extern "C" int caae_hpr_select(int b, int n, const float* flipped, const float* 
   CAAE_RETURN_IF(b < 0 || n <= 0 || n > SY_MAXN || take <= 0 || org_stride_pts < n, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!flipped || !org || !out_pts || !num_vis, CAAE_E_NULLPTR);
-  size_t smem = (size_t)n * (3 * sizeof(double) + sizeof(unsigned short) + 2) + 16;
+  size_t smem = (size_t)n * (5 * sizeof(double) + sizeof(float4) + 2 * sizeof(unsigned short) + 4) + 8 +
+                sizeof(int) * (2 * SY_G * SY_G + 1) + 16;
   smem = (smem + 15) & ~(size_t)15;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(hpr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
