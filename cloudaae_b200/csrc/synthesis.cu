@@ -190,6 +190,7 @@ struct HprShared {
   const unsigned short* order;      // point ids sorted by grid cell
   const unsigned char *cellx, *celly;
   const int* cell_start;            // [SY_G*SY_G + 1]
+  const unsigned char* dup;         // 2 = exact copy of a lower-index point (not a constraint)
   double kappa;
   int n;
 };
@@ -253,7 +254,7 @@ __device__ bool hpr_clip_warp(const HprShared& h, const Nbhd& nb, int i, double 
     if (j != i) clip(j);
   }
   for (int j = lane; j < j_end; j += 32)
-    if (!in_nbhd(h, nb, j)) clip(j);
+    if (!in_nbhd(h, nb, j) && h.dup[j] != 2) clip(j);
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) { lo = fmax(lo, shfl_xor_d(lo, m)); hi = fmin(hi, shfl_xor_d(hi, m)); }
   if (lo > hi) return false;
@@ -277,7 +278,7 @@ __device__ bool hpr_lp_warp(const HprShared& h, const Nbhd& nb, int i, int j_to,
     const int q = pos + lane;
     int j = -1;
     if (q < m) j = nbhd_elem(h, nb, q);
-    else if (q < total) { j = q - m; if (in_nbhd(h, nb, j)) j = -1; }
+    else if (q < total) { j = q - m; if (in_nbhd(h, nb, j) || h.dup[j] == 2) j = -1; }
     bool viol = false, hidden = false;
     double du = 0.0, dv = 0.0, rhs = 0.0;
     if (j >= 0 && j != i) {
@@ -363,7 +364,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
     int cx = (int)(((float)U[i] - s_box[0]) / s_box[2] * SY_G), cy = (int)(((float)V[i] - s_box[1]) / s_box[3] * SY_G);
     cx = min(max(cx, 0), SY_G - 1); cy = min(max(cy, 0), SY_G - 1);
     cellx[i] = (unsigned char)cx; celly[i] = (unsigned char)cy;
-    flag[i] = 0; dirty[i] = 0;
+    flag[i] = 0;
     atomicAdd(&cell_fill[cy * SY_G + cx], 1);
   }
   __syncthreads();
@@ -389,10 +390,52 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
   __syncthreads();
   for (int i = tid; i < n; i += SY_THREADS) order[atomicAdd(&cell_fill[celly[i] * SY_G + cellx[i]], 1)] = (unsigned short)i;
   __syncthreads();
+  // ---- exact duplicates (the shipped models contain some: class 17 stores 574 copies of one point):
+  // only the lowest index of identical points takes part; the copies are hidden by definition and are
+  // removed from the cell lists so they cost nothing as constraints.
+  for (int i = tid; i < n; i += SY_THREADS) {
+    const int cell = celly[i] * SY_G + cellx[i];
+    const float x = f[i * 3 + 0], y = f[i * 3 + 1], z = f[i * 3 + 2];
+    bool dup = false;
+    for (int k = cell_start[cell]; k < cell_start[cell + 1] && !dup; ++k) {
+      const int j = order[k];
+      dup = j < i && f[j * 3 + 0] == x && f[j * 3 + 1] == y && f[j * 3 + 2] == z;
+    }
+    dirty[i] = dup ? 2 : 0;
+  }
+  __syncthreads();
+  cell_fill[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += SY_THREADS)
+    if (dirty[i] != 2) atomicAdd(&cell_fill[celly[i] * SY_G + cellx[i]], 1);
+  __syncthreads();
+  {
+    const int v = cell_fill[tid];
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = s_warp_tot[lane];
+      int iw = w;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iw, o); if (lane >= o) iw += t; }
+      s_warp_tot[lane] = iw - w;
+    }
+    __syncthreads();
+    const int excl = s_warp_tot[warp] + inc - v;
+    cell_start[tid] = excl;
+    if (tid == SY_THREADS - 1) cell_start[SY_G * SY_G] = excl + v;
+    cell_fill[tid] = excl;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += SY_THREADS)
+    if (dirty[i] != 2) order[atomicAdd(&cell_fill[celly[i] * SY_G + cellx[i]], 1)] = (unsigned short)i;
+  __syncthreads();
+  const int n_unique = cell_start[SY_G * SY_G];
 
   HprShared h;
   h.U = U; h.V = V; h.W = W; h.order = order; h.cellx = cellx; h.celly = celly; h.cell_start = cell_start;
-  h.kappa = rho; h.n = n;
+  h.kappa = rho; h.n = n; h.dup = dirty;
 
   // ---- phase 1: one WARP per point (dynamic queue, cell order): incremental LP over the point's 3x3
   // cell neighbourhood, where nearly all re-solves happen.  Survivors (~45 %) are queued with their optimum.
@@ -400,7 +443,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
     int t = 0;
     if (lane == 0) t = atomicAdd(&s_queue, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= n) break;
+    if (t >= n_unique) break;
     const int i = order[t];
     Nbhd nb;
     make_nbhd(h, i, s_nb[warp], nb);
@@ -424,7 +467,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
     const int sl = q / spad, sidx = q - sl * spad;
     if (sidx >= nsurv) continue;
     const int i = surv[sidx];
-    if (dirty[i]) continue;
+    if (dirty[i] == 1) continue;
     const float4 fi = F4[i];
     const double sa = SA[sidx], sb = SB[sidx];
     const float saf = (float)sa, sbf = (float)sb;
@@ -439,6 +482,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
       const float dotf = fmaf(saf, duf, sbf * dvf);
       const float tol = 1e-3f + 2e-5f * (fabsf(rhsf) + fabsf(dotf) + kh * r2f);
       if (rhsf - dotf <= -tol) continue;                                  // clearly slack
+      if (dirty[j] == 2) continue;                                        // copy of a lower-index point
       if (abs((int)cellx[j] - cx) <= 1 && abs((int)celly[j] - cy) <= 1) continue;  // handled in phase 1
       const double du = U[j] - U[i], dv = V[j] - V[i];
       const double r2 = du * du + dv * dv, dw = W[j] - W[i];
@@ -459,7 +503,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= nsurv) break;
     const int i = surv[t];
-    if (!dirty[i]) { if (lane == 0) flag[i] = 1; continue; }
+    if (dirty[i] != 1) { if (lane == 0) flag[i] = 1; continue; }
     Nbhd nb;
     make_nbhd(h, i, s_nb[warp], nb);
     double sa = 0.0, sb = 0.0;
@@ -555,3 +599,4 @@ extern "C" int caae_hpr_select(int b, int n, const float* flipped, const float* 
                                                                 flags_out);
   return CAAE_LAUNCH_STATUS();
 }
+
