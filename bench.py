@@ -651,26 +651,27 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    try:
-        if args.workload in ("auto", "train"):
-            result = run_ours_train(args, rank, world, local_rank)
-            if rank == 0:
-                # the metric also asks for FPS / nn_distance achieved GB/s: run the tf_ops microbench
-                # (BASELINE configs[1]) on rank 0 after the timed region and attach its kernel table
-                class OpsArgs:
-                    steps, warmup = 30, 3
-                ops = run_ours_ops(OpsArgs, 0, 1, local_rank, with_cpu_baseline=False)
-                result["ops_microbench"] = {"segments_per_s": ops["value"], "ms_per_pass": ops["ms_per_step"],
-                                            "kernels": ops["kernels"], "config": ops["config"]}
-                result["cpu_baseline"] = cpu_baseline_train()
-        else:
-            result = run_ours_ops(args, rank, world, local_rank)
-        if rank == 0:
-            print(json.dumps(result), flush=True)
-    finally:
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
+    if args.workload in ("auto", "train"):
+        result = run_ours_train(args, rank, world, local_rank)
+        if rank == 0 and world == 1:
+            # the metric also asks for FPS / nn_distance achieved GB/s: run the tf_ops microbench
+            # (BASELINE configs[1]) on rank 0 after the timed region and attach its kernel table
+            class OpsArgs:
+                steps, warmup = 30, 3
+            ops = run_ours_ops(OpsArgs, 0, 1, local_rank, with_cpu_baseline=False)
+            result["ops_microbench"] = {"segments_per_s": ops["value"], "ms_per_pass": ops["ms_per_step"],
+                                        "kernels": ops["kernels"], "config": ops["config"]}
+            result["cpu_baseline"] = cpu_baseline_train()
+    else:
+        result = run_ours_ops(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        # NCCL communicators referenced by a live CUDA graph make destroy_process_group() block; the
+        # timed region is over and the line is printed, so leave without tearing the group down.
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
