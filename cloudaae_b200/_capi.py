@@ -79,6 +79,7 @@ _SPECIAL = {
     "caae_fps_scratch_bytes": ([_int, _int], ctypes.c_size_t),
     "caae_edge_parts": ([_int, _int, _int, _int, _int], _int),
     "caae_col_parts": ([_int], _int),
+    "caae_debug_hpr_timing": ([_ptr], _int),
     "caae_gemm_tf32_supported": ([_int, _int, _int, _int, _int, _ptr, _int, _ptr, _int], _int),
 }
 

@@ -27,13 +27,12 @@
 //
 // One CTA (1024 threads) per cloud; everything a cloud needs lives in shared memory.
 #include "common.cuh"
+#include "hpr_lp.cuh"
 
 namespace caae {
 
 constexpr int SY_THREADS = 1024;
-constexpr int SY_G = 32;                 // grid cells per axis over the (u,v) bounding box (one cell per thread)
-constexpr int SY_MAXN = 4096;            // points per cloud the HPR kernel supports
-constexpr int SY_LOCAL = 9;              // phase 1 visits the 3x3 cell neighbourhood
+constexpr int SY_MAXN = 2688;            // points per cloud the HPR kernel supports (82 B of shared memory each)
 
 // ---- Philox4x32-10 -----------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
@@ -173,6 +172,44 @@ synth_points_kernel(int nm, int no, const float* __restrict__ models, const int*
 }
 
 // ---- hidden point removal + visible-prefix selection ---------------------------------------------
+//
+// Shared-memory layout of one cloud (n input points, all arrays sized by n):
+//   Us, Vs, Ws   fp64   lifted coordinates, SORTED by grid cell (row-major cells, ascending index inside a cell)
+//   SA, SB       fp64   set-up: (u, v) by original index; afterwards the survivors' optima, by survivor slot
+//   F4           f32x4  sorted fp32 copy (u, v, w + rho, -) for the verification filter; the 4th word of
+//                       entry `slot` holds the survivor's worst-violator key of the current round
+//   id           u16    sorted position -> original index
+//   surv         u16    set-up: unordered cell fill; afterwards survivor slot -> sorted position
+//   vlist        u16    set-up: original index -> cell; afterwards the slots to verify in this round
+//   wlist        u16    the slots to re-solve in this round
+//   ext          u16x8  per survivor slot: positions of the violated far constraints added to its LP
+//   flag         u8     original index -> visible
+//   state        u8     set-up: duplicate marks; afterwards per slot: number of ext entries, or kHidden
+constexpr int SY_EXTRA = 8;     // far constraints a survivor's LP can take before the full re-solve
+constexpr int SY_BYTES_PER_POINT = 5 * 8 + 16 + 4 * 2 + SY_EXTRA * 2 + 2;
+constexpr unsigned char kHidden = 0xFF;
+static_assert(SY_MAXN < (1 << hpr::kPosBits), "violation_key stores the position in 12 bits");
+
+// Exclusive scan of one int per thread over the 1024-thread CTA; returns the exclusive prefix, `total` = sum.
+__device__ __forceinline__ int block_excl_scan(int v, int* s_warp_tot, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  __syncthreads();  // s_warp_tot may still be read by a previous call
+  if (lane == 31) s_warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = s_warp_tot[lane];
+    int iw = w;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iw, o); if (lane >= o) iw += t; }
+    s_warp_tot[lane] = iw - w;
+    if (lane == 31) s_warp_tot[32] = iw;
+  }
+  __syncthreads();
+  total = s_warp_tot[32];
+  return s_warp_tot[warp] + inc - v;
+}
+
 __device__ __forceinline__ double shfl_d(double v, int src) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
@@ -184,154 +221,151 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) {
   return __hiloint2double(hi, lo);
 }
 
-// Everything the per-point LP needs, in shared memory.
-struct HprShared {
-  const double *U, *V, *W;          // lifted coordinates (paraboloid-shifted), fp64
-  const unsigned short* order;      // point ids sorted by grid cell
-  const unsigned char *cellx, *celly;
-  const int* cell_start;            // [SY_G*SY_G + 1]
-  const unsigned char* dup;         // 2 = exact copy of a lower-index point (not a constraint)
-  double kappa;
-  int n;
-};
-
-// The constraint sequence of point i is: its 3x3 cell neighbourhood (9 cell segments of `order`),
-// then every point OUTSIDE that neighbourhood in index order.  Nbhd caches the 9 segments.
-struct Nbhd {
-  int* start;  // [SY_LOCAL]      per-warp shared-memory scratch
-  int* pre;    // [SY_LOCAL + 1]  exclusive prefix of the segment lengths
-  int cx, cy;
-};
-__device__ __forceinline__ void make_nbhd(const HprShared& h, int i, int* scratch, Nbhd& nb) {
-  nb.start = scratch; nb.pre = scratch + SY_LOCAL;
-  nb.cx = h.cellx[i]; nb.cy = h.celly[i];
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) {
-    int run = 0;
-    nb.pre[0] = 0;
-    for (int o = 0; o < SY_LOCAL; ++o) {
-      const int x = nb.cx + (o % 3) - 1, y = nb.cy + (o / 3) - 1;
-      const bool valid = x >= 0 && x < SY_G && y >= 0 && y < SY_G;
-      const int cell = valid ? y * SY_G + x : 0;
-      nb.start[o] = valid ? h.cell_start[cell] : 0;
-      run += valid ? h.cell_start[cell + 1] - h.cell_start[cell] : 0;
-      nb.pre[o + 1] = run;
+// Persistent LP solver: every 8-lane GROUP of the calling warp runs the incremental LP of one point
+// (the math of hpr::lp_lane, eight constraints per step), and fetches its next point the moment it
+// finishes one, so the four groups of a warp never wait for each other.  One loop body serves the
+// groups that are scanning and the groups that are clipping; the group-wide exchanges (broadcast of a
+// violated constraint, reduction of a clip interval) run only in the steps where some group needs one.
+//   fetch(want, gbase, self, seq, tag, sa, sb, p0): warp-uniform call; groups with want = true receive
+//        their next point (sorted position `self`, its constraint sequence, a caller tag, and the state
+//        to resume from: optimum (sa, sb) of the first p0 constraints) or self = -1 when the work list
+//        is exhausted.
+//   finish(fin, gbase, self, tag, status, sa, sb): warp-uniform call; groups with fin = true report.
+template <class Fetch, class Finish>
+__device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch, Finish finish) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31, g = lane & 7, gbase = lane & ~7;
+  hpr::RangesPlusList seq;
+  int self = -1, tag = 0, L = 0;
+  bool exhausted = false;
+  double ui = 0.0, vi = 0.0, wi = 0.0, sa = 0.0, sb = 0.0;
+  const double hk = 0.5 * h.kappa;
+  int p = 0, q = -1, qend = 0;
+  double p0a = 0.0, p0b = 0.0, da = 0.0, db = 0.0;
+  double ln = -1.0, ld = 0.0, hn = 1.0, hd = 0.0;
+  bool infeas = false;
+  while (true) {
+    // ---- groups without a point fetch one
+    const bool want = self < 0 && !exhausted;
+    if (__any_sync(kFull, want)) {
+      fetch(want, gbase, self, seq, tag, sa, sb, p);
+      if (want) {
+        if (self < 0) exhausted = true;
+        else { L = seq.length(); ui = h.U[self]; vi = h.V[self]; wi = h.W[self]; q = -1; }
+      }
+    }
+    if (__all_sync(kFull, self < 0)) break;
+    const bool busy = self >= 0;
+    // ---- one step: eight constraints of the scan or of the clip
+    const bool clipping = q >= 0;
+    const int cur = (clipping ? q : p) + g;
+    const int j = (busy && cur < (clipping ? qend : L)) ? seq(cur) : -1;
+    const bool valid = j >= 0 && j != self;
+    double du = 0.0, dv = 0.0, dw = 0.0, r2 = 0.0, rhs = 0.0;
+    if (valid) {
+      du = h.U[j] - ui; dv = h.V[j] - vi; dw = h.W[j] - wi;
+      r2 = du * du + dv * dv;
+      rhs = dw - hk * r2;
+    }
+    const bool viol = valid && !clipping && r2 != 0.0 && (rhs - (sa * du + sb * dv) > 0.0);
+    const bool hid = valid && !clipping && r2 == 0.0 && (dw > 0.0 || (dw == 0.0 && h.id[j] < h.id[self]));
+    const unsigned bv = (__ballot_sync(kFull, viol) >> gbase) & 0xFFu;
+    const unsigned bh = (__ballot_sync(kFull, hid) >> gbase) & 0xFFu;
+    if (valid && clipping && r2 != 0.0) {
+      const double den = da * du + db * dv, num = rhs - (p0a * du + p0b * dv);
+      if (den > 0.0) { if (num * ld > ln * den) { ln = num; ld = den; } }
+      else if (den < 0.0) { const double nn = -num, dd = -den; if (nn * hd < hn * dd) { hn = nn; hd = dd; } }
+      else if (num > 0.0) infeas = true;
+    }
+    int status = -1;                 // >= 0: the group's point is decided in this step
+    bool start_clip = false, end_clip = false;
+    int fv = 0;
+    if (busy) {
+      if (!clipping) {
+        fv = bv ? __ffs(bv) - 1 : 8;
+        const int fh = bh ? __ffs(bh) - 1 : 8;
+        if (fh < fv) status = hpr::kLpHidden;          // a "hidden" verdict earlier than any violation
+        else if (fv == 8) { p += 8; if (p >= L) status = hpr::kLpVisible; }
+        else start_clip = true;
+      } else {
+        q += 8;
+        end_clip = q >= qend;
+      }
+    }
+    if (__any_sync(kFull, start_clip)) {
+      const int src = gbase + (start_clip ? fv : 0);
+      const double bdu = shfl_d(du, src), bdv = shfl_d(dv, src), brhs = shfl_d(rhs, src);
+      if (start_clip) {   // the new optimum lies on the violated constraint's boundary line p0 + t (da, db)
+        const double inv = brhs / (bdu * bdu + bdv * bdv);
+        p0a = bdu * inv; p0b = bdv * inv; da = -bdv; db = bdu;
+        ln = -1.0; ld = 0.0; hn = 1.0; hd = 0.0; infeas = false;
+        qend = p + fv; p = p + fv + 1; q = 0;
+        end_clip = qend == 0;
+      }
+    }
+    if (__any_sync(kFull, end_clip)) {
+      double lo = ld > 0.0 ? ln / ld : -INFINITY, hi = hd > 0.0 ? hn / hd : INFINITY;
+#pragma unroll
+      for (int m = 1; m < 8; m <<= 1) { lo = fmax(lo, shfl_xor_d(lo, m)); hi = fmin(hi, shfl_xor_d(hi, m)); }
+      const unsigned binf = (__ballot_sync(kFull, infeas) >> gbase) & 0xFFu;
+      if (end_clip) {
+        if (binf || lo > hi) status = hpr::kLpHidden;
+        else {
+          const double t = fmin(fmax(0.0, lo), hi);
+          sa = p0a + t * da; sb = p0b + t * db; q = -1;
+          if (p >= L) status = hpr::kLpVisible;
+        }
+      }
+    }
+    const bool fin = status >= 0;
+    if (__any_sync(kFull, fin)) {
+      finish(fin, gbase, self, tag, status, sa, sb);
+      if (fin) self = -1;
     }
   }
-  __syncwarp();
-}
-__device__ __forceinline__ int nbhd_elem(const HprShared& h, const Nbhd& nb, int e) {
-  int o = 0;
-#pragma unroll
-  for (int q = 1; q < SY_LOCAL; ++q) o += (e >= nb.pre[q]) ? 1 : 0;
-  return h.order[nb.start[o] + (e - nb.pre[o])];
-}
-__device__ __forceinline__ bool in_nbhd(const HprShared& h, const Nbhd& nb, int j) {
-  return abs((int)h.cellx[j] - nb.cx) <= 1 && abs((int)h.celly[j] - nb.cy) <= 1;
 }
 
-// Warp-cooperative clip: minimum-norm point of the boundary line of constraint (du,dv,rhs) of point i,
-// subject to the first `e_end` neighbourhood constraints and the non-neighbourhood points of index
-// < j_end.  All arguments are warp-uniform; all lanes return the same result.
-__device__ bool hpr_clip_warp(const HprShared& h, const Nbhd& nb, int i, double ui, double vi, double wi, double du,
-                              double dv, double rhs, int e_end, int j_end, double& sa, double& sb) {
-  const int lane = threadIdx.x & 31;
-  const double r2 = du * du + dv * dv;
-  const double p0a = du * rhs / r2, p0b = dv * rhs / r2, da = -dv, db = du;
-  double lo = -INFINITY, hi = INFINITY;
-  auto clip = [&](int j) {
-    const double eu = h.U[j] - ui, ev = h.V[j] - vi;
-    const double s2 = eu * eu + ev * ev;
-    if (s2 == 0.0) return;
-    const double rk = (h.W[j] - wi) - 0.5 * h.kappa * s2;
-    const double den = da * eu + db * ev, num = rk - (p0a * eu + p0b * ev);
-    if (den > 0.0) lo = fmax(lo, num / den);
-    else if (den < 0.0) hi = fmin(hi, num / den);
-    else if (num > 0.0) lo = INFINITY;
-  };
-  for (int e = lane; e < e_end; e += 32) {
-    const int j = nbhd_elem(h, nb, e);
-    if (j != i) clip(j);
-  }
-  for (int j = lane; j < j_end; j += 32)
-    if (!in_nbhd(h, nb, j) && h.dup[j] != 2) clip(j);
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) { lo = fmax(lo, shfl_xor_d(lo, m)); hi = fmin(hi, shfl_xor_d(hi, m)); }
-  if (lo > hi) return false;
-  const double t = fmin(fmax(0.0, lo), hi);
-  sa = p0a + t * da; sb = p0b + t * db;
-  return true;
-}
-
-// One warp runs the incremental LP of point i over elements [e_from, m) of its neighbourhood and then
-// (when j_to > 0) over the non-neighbourhood points [0, j_to).  32 constraints are tested per step; the
-// first violated one (in sequence order) triggers a cooperative clip and the scan resumes right after
-// it.  Returns false when the point is proven hidden; (sa, sb) is the running optimum.
-__device__ bool hpr_lp_warp(const HprShared& h, const Nbhd& nb, int i, int j_to, double& sa, double& sb) {
-  const int lane = threadIdx.x & 31;
-  const double ui = h.U[i], vi = h.V[i], wi = h.W[i];
-  const int m = nb.pre[SY_LOCAL];
-  // pos runs over the concatenated sequence: [0, m) neighbourhood elements, [m, m + j_to) = index j = pos - m
-  const int total = m + j_to;
-  int pos = 0;
-  while (pos < total) {
-    const int q = pos + lane;
-    int j = -1;
-    if (q < m) j = nbhd_elem(h, nb, q);
-    else if (q < total) { j = q - m; if (in_nbhd(h, nb, j) || h.dup[j] == 2) j = -1; }
-    bool viol = false, hidden = false;
-    double du = 0.0, dv = 0.0, rhs = 0.0;
-    if (j >= 0 && j != i) {
-      du = h.U[j] - ui; dv = h.V[j] - vi;
-      const double r2 = du * du + dv * dv;
-      const double dw = h.W[j] - wi;
-      if (r2 == 0.0) hidden = dw > 0.0 || (dw == 0.0 && j < i);   // same direction: nearer / lower index stays
-      else { rhs = dw - 0.5 * h.kappa * r2; viol = rhs - (sa * du + sb * dv) > 0.0; }
-    }
-    const unsigned mv = __ballot_sync(0xffffffffu, viol), mh = __ballot_sync(0xffffffffu, hidden);
-    const int fv = mv ? __ffs(mv) - 1 : 32, fh = mh ? __ffs(mh) - 1 : 32;
-    if (fh < fv) return false;                 // a "hidden" verdict earlier in the sequence than any violation
-    if (fv == 32) { pos += 32; continue; }
-    du = shfl_d(du, fv); dv = shfl_d(dv, fv); rhs = shfl_d(rhs, fv);
-    const int qv = pos + fv;                   // sequence position of the violated constraint
-    if (!hpr_clip_warp(h, nb, i, ui, vi, wi, du, dv, rhs, min(qv, m), max(qv - m, 0), sa, sb)) return false;
-    pos = qv + 1;
-  }
-  return true;
-}
-
-constexpr int SY_SLICE = 256;  // phase-2 verification: points per (survivor, slice) work item
+// Diagnostics: per CTA (modulo 512) clock64 deltas {set-up, phase 1, first verification, remaining rounds,
+// compaction+select}, then {survivors, rounds, re-solved in round 0}; read with caae_debug_hpr_timing.
+__device__ long long g_hpr_timing[512 * 8];
 
 __global__ void __launch_bounds__(SY_THREADS)
 hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restrict__ org, int org_stride_pts, int take,
                   const float* __restrict__ pad_uniform, float* __restrict__ out_pts, int* __restrict__ num_vis,
                   unsigned char* __restrict__ flags_out) {
+  static_assert(hpr::G * hpr::G == SY_THREADS, "one grid cell per thread");
+  constexpr int G = hpr::G;
   extern __shared__ __align__(16) unsigned char sy_smem[];
-  double* U = reinterpret_cast<double*>(sy_smem);
-  double* V = U + n;
-  double* W = V + n;
-  double* SA = W + n;                                          // survivors' optima after phase 1
+  double* Us = reinterpret_cast<double*>(sy_smem);
+  double* Vs = Us + n;
+  double* Ws = Vs + n;
+  double* SA = Ws + n;
   double* SB = SA + n;
-  float4* F4 = reinterpret_cast<float4*>(SB + n);              // fp32 copy (u, v, w - w_ref, 0) for the phase-2 filter
-  unsigned short* order = reinterpret_cast<unsigned short*>(F4 + n);
-  unsigned short* surv = order + n;
-  unsigned char* cellx = reinterpret_cast<unsigned char*>(surv + n);
-  unsigned char* celly = cellx + n;
-  unsigned char* flag = celly + n;
-  unsigned char* dirty = flag + n;
-  int* cell_start = reinterpret_cast<int*>(dirty + ((n + 3) & ~3));   // [SY_G*SY_G + 1]
-  int* cell_fill = cell_start + SY_G * SY_G + 1;                       // [SY_G*SY_G]
-  int* ids = reinterpret_cast<int*>(sy_smem);  // reuses the U region after the LP phases
+  float4* F4 = reinterpret_cast<float4*>(SB + n);
+  unsigned short* id = reinterpret_cast<unsigned short*>(F4 + n);
+  unsigned short* surv = id + n;
+  unsigned short* vlist = surv + n;
+  unsigned short* wlist = vlist + n;
+  unsigned short* ext = wlist + n;                                     // [n][SY_EXTRA]
+  unsigned char* flag = reinterpret_cast<unsigned char*>(ext + (size_t)n * SY_EXTRA);
+  unsigned char* state = flag + n;
+  int* cell_start = reinterpret_cast<int*>(state + ((n + 3) & ~3));    // [G*G + 1]
+  int* cell_fill = cell_start + G * G + 1;                             // [G*G]
+  int* ids = reinterpret_cast<int*>(sy_smem);                          // reuses the Us region after the LP phases
+  unsigned short* tmp = surv;                                          // set-up aliases
+  unsigned short* cell_of_orig = vlist;
   __shared__ float s_redf[32];
-  __shared__ int s_warp_tot[32];
-  __shared__ float s_box[4];
-  __shared__ int s_count, s_queue;
-  __shared__ int s_nb[SY_THREADS / 32][2 * SY_LOCAL + 2];
+  __shared__ int s_warp_tot[33];
+  __shared__ float s_box[4], s_fzrow[hpr::G], s_fzmax;
+  __shared__ int s_count, s_queue, s_nlist, s_nwork;
 
-  const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const float* __restrict__ f = flipped + (size_t)cloud * n * 3;
 
-  // ---- rho = max |f|, then lifted coordinates in fp64
+  long long tk[6] = {0, 0, 0, 0, 0, 0};
+  int dbg_rounds = 0, dbg_resolved = 0;
+  if (tid == 0) tk[0] = clock64();
+  // ---- rho = max |f|; (u, v) in fp64 by original index; bounding box of (u, v)
   float nmax = 0.f;
   for (int i = tid; i < n; i += SY_THREADS) {
     const float x = f[i * 3 + 0], y = f[i * 3 + 1], z = f[i * 3 + 2];
@@ -341,12 +375,9 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
   const double rho = (double)nmax;
   float umin = 3.4e38f, umax = -3.4e38f, vmin = 3.4e38f, vmax = -3.4e38f;
   for (int i = tid; i < n; i += SY_THREADS) {
-    const double x = (double)f[i * 3 + 0], y = (double)f[i * 3 + 1], z = (double)f[i * 3 + 2];
-    const double u = x / z, v = y / z;
-    U[i] = u; V[i] = v;
-    const double w = -rho * rho / z + 0.5 * rho * (u * u + v * v);  // paraboloid-shifted lift
-    W[i] = w;
-    F4[i] = make_float4((float)u, (float)v, (float)(w + rho), 0.f);  // w ~ -rho: recentre before rounding to fp32
+    const double z = (double)f[i * 3 + 2];
+    const double u = (double)f[i * 3 + 0] / z, v = (double)f[i * 3 + 1] / z;
+    SA[i] = u; SB[i] = v;
     umin = fminf(umin, (float)u); umax = fmaxf(umax, (float)u);
     vmin = fminf(vmin, (float)v); vmax = fmaxf(vmax, (float)v);
   }
@@ -354,162 +385,275 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
   umin = -block_max(-umin, s_redf); vmin = -block_max(-vmin, s_redf);
   if (tid == 0) {
     s_box[0] = umin; s_box[1] = vmin; s_box[2] = fmaxf(umax - umin, 1e-30f); s_box[3] = fmaxf(vmax - vmin, 1e-30f);
-    s_count = 0; s_queue = 0;
+    s_count = 0; s_queue = 0; s_nlist = 0;
   }
-  for (int c = tid; c < SY_G * SY_G; c += SY_THREADS) cell_fill[c] = 0;
+  cell_fill[tid] = 0;
   __syncthreads();
 
-  // ---- counting sort of the points into grid cells
+  // ---- cells; unordered fill of the cell lists
   for (int i = tid; i < n; i += SY_THREADS) {
-    int cx = (int)(((float)U[i] - s_box[0]) / s_box[2] * SY_G), cy = (int)(((float)V[i] - s_box[1]) / s_box[3] * SY_G);
-    cx = min(max(cx, 0), SY_G - 1); cy = min(max(cy, 0), SY_G - 1);
-    cellx[i] = (unsigned char)cx; celly[i] = (unsigned char)cy;
+    int cx = (int)(((float)SA[i] - s_box[0]) / s_box[2] * G), cy = (int)(((float)SB[i] - s_box[1]) / s_box[3] * G);
+    cx = min(max(cx, 0), G - 1); cy = min(max(cy, 0), G - 1);
+    const int c = cy * G + cx;
+    cell_of_orig[i] = (unsigned short)c;
     flag[i] = 0;
-    atomicAdd(&cell_fill[cy * SY_G + cx], 1);
+    atomicAdd(&cell_fill[c], 1);
   }
   __syncthreads();
-  {  // exclusive scan of SY_G*SY_G (= SY_THREADS) counts, one per thread
-    static_assert(SY_G * SY_G == SY_THREADS, "one cell per thread");
-    const int v = cell_fill[tid];
-    int inc = v;
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      const int w = s_warp_tot[lane];
-      int iw = w;
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iw, o); if (lane >= o) iw += t; }
-      s_warp_tot[lane] = iw - w;
-    }
-    __syncthreads();
-    const int excl = s_warp_tot[warp] + inc - v;
+  int total;
+  {
+    const int excl = block_excl_scan(cell_fill[tid], s_warp_tot, total);
     cell_start[tid] = excl;
-    if (tid == SY_THREADS - 1) cell_start[SY_G * SY_G] = excl + v;
+    if (tid == SY_THREADS - 1) cell_start[G * G] = total;
     cell_fill[tid] = excl;
   }
   __syncthreads();
-  for (int i = tid; i < n; i += SY_THREADS) order[atomicAdd(&cell_fill[celly[i] * SY_G + cellx[i]], 1)] = (unsigned short)i;
+  for (int i = tid; i < n; i += SY_THREADS) tmp[atomicAdd(&cell_fill[cell_of_orig[i]], 1)] = (unsigned short)i;
   __syncthreads();
   // ---- exact duplicates (the shipped models contain some: class 17 stores 574 copies of one point):
-  // only the lowest index of identical points takes part; the copies are hidden by definition and are
-  // removed from the cell lists so they cost nothing as constraints.
+  // only the lowest index of identical points takes part; the copies are hidden by definition.
   for (int i = tid; i < n; i += SY_THREADS) {
-    const int cell = celly[i] * SY_G + cellx[i];
+    const int c = cell_of_orig[i];
     const float x = f[i * 3 + 0], y = f[i * 3 + 1], z = f[i * 3 + 2];
     bool dup = false;
-    for (int k = cell_start[cell]; k < cell_start[cell + 1] && !dup; ++k) {
-      const int j = order[k];
+    for (int k = cell_start[c]; k < cell_start[c + 1] && !dup; ++k) {
+      const int j = tmp[k];
       dup = j < i && f[j * 3 + 0] == x && f[j * 3 + 1] == y && f[j * 3 + 2] == z;
     }
-    dirty[i] = dup ? 2 : 0;
+    state[i] = dup ? 2 : 0;
   }
-  __syncthreads();
   cell_fill[tid] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += SY_THREADS)
-    if (dirty[i] != 2) atomicAdd(&cell_fill[celly[i] * SY_G + cellx[i]], 1);
+    if (state[i] != 2) atomicAdd(&cell_fill[cell_of_orig[i]], 1);
   __syncthreads();
+  int n_unique;
   {
-    const int v = cell_fill[tid];
-    int inc = v;
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      const int w = s_warp_tot[lane];
-      int iw = w;
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iw, o); if (lane >= o) iw += t; }
-      s_warp_tot[lane] = iw - w;
-    }
-    __syncthreads();
-    const int excl = s_warp_tot[warp] + inc - v;
-    cell_start[tid] = excl;
-    if (tid == SY_THREADS - 1) cell_start[SY_G * SY_G] = excl + v;
-    cell_fill[tid] = excl;
+    const int excl = block_excl_scan(cell_fill[tid], s_warp_tot, n_unique);
+    cell_fill[tid] = excl;  // start of the cell in the final order
   }
   __syncthreads();
-  for (int i = tid; i < n; i += SY_THREADS)
-    if (dirty[i] != 2) order[atomicAdd(&cell_fill[celly[i] * SY_G + cellx[i]], 1)] = (unsigned short)i;
-  __syncthreads();
-  const int n_unique = cell_start[SY_G * SY_G];
-
-  HprShared h;
-  h.U = U; h.V = V; h.W = W; h.order = order; h.cellx = cellx; h.celly = celly; h.cell_start = cell_start;
-  h.kappa = rho; h.n = n; h.dup = dirty;
-
-  // ---- phase 1: one WARP per point (dynamic queue, cell order): incremental LP over the point's 3x3
-  // cell neighbourhood, where nearly all re-solves happen.  Survivors (~45 %) are queued with their optimum.
-  while (true) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(&s_queue, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= n_unique) break;
-    const int i = order[t];
-    Nbhd nb;
-    make_nbhd(h, i, s_nb[warp], nb);
-    double sa = 0.0, sb = 0.0;
-    if (hpr_lp_warp(h, nb, i, 0, sa, sb) && lane == 0) {
-      const int slot = atomicAdd(&s_count, 1);
-      surv[slot] = (unsigned short)i; SA[slot] = sa; SB[slot] = sb;
+  // ---- final order: cell-major, ascending original index inside a cell (deterministic)
+  for (int i = tid; i < n; i += SY_THREADS) {
+    if (state[i] == 2) continue;
+    const int c = cell_of_orig[i];
+    int rank = 0;
+    for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
+      const int j = tmp[k];
+      rank += (j < i && state[j] != 2) ? 1 : 0;
     }
+    id[cell_fill[c] + rank] = (unsigned short)i;
+  }
+  __syncthreads();
+  cell_start[tid] = cell_fill[tid];
+  if (tid == 0) cell_start[G * G] = n_unique;
+  __syncthreads();
+  // ---- lifted coordinates in sorted order
+  for (int p = tid; p < n_unique; p += SY_THREADS) {
+    const int i = id[p];
+    const double u = SA[i], v = SB[i], z = (double)f[i * 3 + 2];
+    const double w = -rho * rho / z + 0.5 * rho * (u * u + v * v);  // paraboloid-shifted lift (hpr::lift)
+    Us[p] = u; Vs[p] = v; Ws[p] = w;
+    F4[p] = make_float4((float)u, (float)v, (float)(w + rho), 0.f);  // w ~ -rho: recentre before rounding to fp32
+  }
+  __syncthreads();
+  if (tid < G) {   // per grid row: maximum of the fp32 (w + rho) — the verification's bound on w_j
+    float m = -3.4e38f;
+    for (int p = cell_start[tid * G]; p < cell_start[(tid + 1) * G]; ++p) m = fmaxf(m, F4[p].z);
+    s_fzrow[tid] = m;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));   // tid < G = one warp
+    if (tid == 0) s_fzmax = m;
   }
   __syncthreads();
 
-  // ---- phase 2: verify every survivor's optimum against all points, as (survivor, 256-point slice)
-  // work items.  Lanes of a warp share the slice (broadcast LDS.128 of the fp32 copy); a conservative
-  // fp32 evaluation dismisses constraints that are clearly slack, the few within `tol` of tight are
-  // re-evaluated in fp64; a genuine violation marks the survivor dirty for phase 3.
+  hpr::View h;
+  h.U = Us; h.V = Vs; h.W = Ws; h.id = id; h.cell_start = cell_start; h.kappa = rho; h.n_unique = n_unique;
+
+  if (tid == 0) tk[1] = clock64();
+  // ---- phase 1: incremental LP of every point over its 3x3 cell neighbourhood (own grid row first),
+  // eight lanes per point, points handed out in sorted order from a queue.  Survivors (~40 %) are
+  // recorded with their optimum.
+  {
+    auto fetch = [&](bool want, int gbase, int& self, hpr::RangesPlusList& seq, int& tag, double& sa, double& sb, int& p0) {
+      int t = 0;
+      if (want && (lane & 7) == 0) t = atomicAdd(&s_queue, 1);
+      t = __shfl_sync(0xffffffffu, t, gbase);
+      if (want) {
+        sa = 0.0; sb = 0.0; p0 = 0;
+        if (t < n_unique) {
+          const int c = hpr::find_cell(cell_start, t);
+          int A[3], B[3];
+          hpr::nbhd_ranges(cell_start, c % G, c / G, A, B);
+          seq = hpr::RangesPlusList(A, B, nullptr, 0);
+          self = t; tag = 0;
+        } else self = -1;
+      }
+    };
+    auto finish = [&](bool fin, int gbase, int self, int tag, int status, double sa, double sb) {
+      const bool alive = fin && status == hpr::kLpVisible;
+      int slot = 0;
+      if (alive && (lane & 7) == 0) {
+        slot = atomicAdd(&s_count, 1);
+        surv[slot] = (unsigned short)self; SA[slot] = sa; SB[slot] = sb; state[slot] = 0;
+      }
+    };
+    hpr_solve_groups(h, fetch, finish);
+  }
+  __syncthreads();
+
+  // ---- phases 2 / 3, in rounds.  Verify: every listed survivor's optimum against all points, as
+  // (survivor, 256-position slice) work items; lanes of a warp share the slice (broadcast LDS.128 of the
+  // fp32 copy); a conservative fp32 evaluation dismisses constraints that are clearly slack, the few
+  // within `tol` of tight are re-evaluated in fp64 and the worst genuine violation is recorded in the
+  // slot's key.  Re-solve: one thread per violated survivor adds that constraint to its LP (neighbourhood
+  // + added constraints) and solves it again; it is verified again in the next round.  A survivor is
+  // visible once a verification finds nothing.
+  if (tid == 0) tk[2] = clock64();
   const int nsurv = s_count;
-  const int spad = (nsurv + 31) & ~31;
-  const int nslice = (n + SY_SLICE - 1) / SY_SLICE;
   const float kh = 0.5f * (float)rho;
-  for (int q = tid; q < spad * nslice; q += SY_THREADS) {
-    const int sl = q / spad, sidx = q - sl * spad;
-    if (sidx >= nsurv) continue;
-    const int i = surv[sidx];
-    if (dirty[i] == 1) continue;
-    const float4 fi = F4[i];
-    const double sa = SA[sidx], sb = SB[sidx];
-    const float saf = (float)sa, sbf = (float)sb;
-    const int cx = cellx[i], cy = celly[i];
-    const int j1 = min(n, (sl + 1) * SY_SLICE);
-    bool bad = false;
-    for (int j = sl * SY_SLICE; j < j1; ++j) {
-      const float4 fj = F4[j];
-      const float duf = fj.x - fi.x, dvf = fj.y - fi.y;
-      const float r2f = fmaf(duf, duf, dvf * dvf);
-      const float rhsf = (fj.z - fi.z) - kh * r2f;
-      const float dotf = fmaf(saf, duf, sbf * dvf);
-      const float tol = 1e-3f + 2e-5f * (fabsf(rhsf) + fabsf(dotf) + kh * r2f);
-      if (rhsf - dotf <= -tol) continue;                                  // clearly slack
-      if (dirty[j] == 2) continue;                                        // copy of a lower-index point
-      if (abs((int)cellx[j] - cx) <= 1 && abs((int)celly[j] - cy) <= 1) continue;  // handled in phase 1
-      const double du = U[j] - U[i], dv = V[j] - V[i];
-      const double r2 = du * du + dv * dv, dw = W[j] - W[i];
-      if (r2 == 0.0) { if (dw > 0.0 || (dw == 0.0 && j < i)) bad = true; continue; }
-      if ((dw - 0.5 * rho * r2) - (sa * du + sb * dv) > 0.0) bad = true;
+  int nlist = nsurv;   // round 0 verifies every survivor (list = identity)
+  bool first = true;
+  while (nlist > 0) {
+    if (tid == 0) { s_nwork = 0; s_queue = 0; s_nlist = 0; }
+    // ---- verify: eight lanes per listed survivor.  A violator of the survivor's optimum s lies inside a
+    // disk around (u_i, v_i) - s/kappa (hpr::verify_disk2, evaluated per grid row with the row's maximum
+    // of w), so the group walks only the grid rows and columns that disk touches, minus the 3x3
+    // neighbourhood phase 1 already enforced — typically a few dozen positions instead of all n.  A
+    // conservative fp32 evaluation dismisses constraints that are clearly slack, the rest are re-evaluated
+    // in fp64 and the worst genuine violation becomes the slot's key.
+    {
+      const int g = lane & 7;
+      const unsigned gmask = 0xFFu << (lane & ~7);
+      const float gx = (float)G / s_box[2], gy = (float)G / s_box[3];
+      const float chh = s_box[3] / (float)G;   // cell height
+      for (int li = tid >> 3; li < nlist; li += SY_THREADS / 8) {
+        const int slot = first ? li : (int)vlist[li];
+        const int ne = state[slot];
+        if (ne == kHidden) continue;
+        const int i = surv[slot];
+        const float4 fi = F4[i];
+        const double sa = SA[slot], sb = SB[slot];
+        const float saf = (float)sa, sbf = (float)sb;
+        const int c = hpr::find_cell(cell_start, i);
+        const int ccx = c % G, ccy = c / G;
+        const int nx0 = max(ccx - 1, 0), nx1 = min(ccx + 1, G - 1);
+        const float ctru = fi.x - saf / (2.f * kh), ctrv = fi.y - sbf / (2.f * kh);   // disk centre
+        unsigned key = 0;
+        bool hidden = false;
+        // rows the disk can touch at all (radius from the cloud-wide maximum of w), then row by row
+        const float rg = sqrtf(fmaxf(hpr::verify_disk2(saf, sbf, fi.z, s_fzmax, kh), 0.f)) * 1.001f;
+        const int cy0 = max((int)floorf((ctrv - rg - s_box[1]) * gy - 0.01f), 0);
+        const int cy1 = min((int)floorf((ctrv + rg - s_box[1]) * gy + 0.01f), G - 1);
+        for (int cy = cy0; cy <= cy1; ++cy) {
+          const bool nrow = cy >= ccy - 1 && cy <= ccy + 1;
+          const float r2 = hpr::verify_disk2(saf, sbf, fi.z, s_fzrow[cy], kh);
+          const float lo = s_box[1] + (float)cy * chh, hi = lo + chh;
+          const float dv = fmaxf(fmaxf(lo - ctrv, ctrv - hi), 0.f) * 0.999f - 0.01f * chh;  // rounded inwards
+          const float w2 = r2 - (dv > 0.f ? dv * dv : 0.f);
+          int cx0 = nx0, cx1 = nx0 - 1;   // empty
+          if (w2 >= 0.f) {
+            const float hw = sqrtf(w2) * 1.001f;
+            cx0 = max((int)floorf((ctru - hw - s_box[0]) * gx - 0.01f), 0);
+            cx1 = min((int)floorf((ctru + hw - s_box[0]) * gx + 0.01f), G - 1);
+          }
+          if (cx1 < cx0) continue;   // (the neighbourhood's own cells need no visit: phase 1 enforced them)
+          // the row's window [ja, jd) minus the neighbourhood's columns [jb, jc) when the row is one of its three
+          const int ja = cell_start[cy * G + cx0], jd = cell_start[cy * G + cx1 + 1];
+          const int jb = nrow ? max(cell_start[cy * G + nx0], ja) : jd;
+          const int jc = nrow ? min(cell_start[cy * G + nx1 + 1], jd) : jd;
+          for (int j0 = ja; j0 < jd; j0 += 8) {
+            const int j = j0 + g;
+            if (j >= jd || (j >= jb && j < jc)) continue;
+            const float4 fj = F4[j];
+            if (hpr::clearly_slack(fi.x, fi.y, fi.z, fj.x, fj.y, fj.z, saf, sbf, kh)) continue;
+            bool known = false;   // already one of the LP's constraints: tight up to rounding, never re-added
+            for (int e = 0; e < ne; ++e) known = known || ext[slot * SY_EXTRA + e] == j;
+            if (known) continue;
+            bool same_dir;
+            const double viol = hpr::violation(h, i, j, sa, sb, same_dir);
+            if (same_dir) { hidden = hidden || Ws[j] > Ws[i] || (Ws[j] == Ws[i] && id[j] < id[i]); continue; }
+            if (viol > 0.0) key = max(key, hpr::violation_key(viol, j));
+          }
+        }
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) {
+          key = max(key, __shfl_xor_sync(gmask, key, m));
+          hidden = __shfl_xor_sync(gmask, (int)hidden, m) || hidden;
+        }
+        if (g == 0) {
+          if (hidden) state[slot] = kHidden;
+          else if (key) F4[slot].w = __uint_as_float(key);
+        }
+      }
     }
-    if (bad) dirty[i] = 1;
+    __syncthreads();
+    // ---- the listed slots whose key is set go to the work list (hidden / verified-clean ones drop out)
+    for (int li = tid; li < nlist; li += SY_THREADS) {
+      const int slot = first ? li : (int)vlist[li];
+      const int ne = state[slot];
+      if (ne == kHidden || __float_as_uint(F4[slot].w) == 0u) continue;
+      if (ne == SY_EXTRA) {   // constraint list full (never seen on the fixtures): the full LP settles it
+        const int i = surv[slot];
+        const int c = hpr::find_cell(cell_start, i);
+        int A[3], B[3], FA[7], FB[7];
+        hpr::nbhd_ranges(cell_start, c % G, c / G, A, B);
+        hpr::full_ranges(A, B, c / G, n_unique, FA, FB);
+        double sa, sb;
+        if (hpr::lp_lane(h, i, hpr::Ranges<7>(FA, FB), sa, sb) != hpr::kLpVisible) state[slot] = kHidden;
+        continue;
+      }
+      wlist[atomicAdd(&s_nwork, 1)] = (unsigned short)slot;
+    }
+    __syncthreads();
+    const int nwork = s_nwork;
+    if (tid == 0 && first) { tk[3] = clock64(); dbg_resolved = nwork; }
+    ++dbg_rounds;
+    // ---- re-solve: the worst violator joins the slot's constraint list and the incremental LP takes
+    // that one more step (clip its boundary line against neighbourhood + list); slots that stay feasible
+    // are verified again in the next round
+    {
+      auto fetch = [&](bool want, int gbase, int& self, hpr::RangesPlusList& seq, int& tag, double& sa, double& sb, int& p0) {
+        int t = 0;
+        if (want && (lane & 7) == 0) t = atomicAdd(&s_queue, 1);
+        t = __shfl_sync(0xffffffffu, t, gbase);
+        if (want) {
+          if (t < nwork) {
+            const int slot = wlist[t];
+            const int i = surv[slot];
+            const int c = hpr::find_cell(cell_start, i);
+            int A[3], B[3];
+            hpr::nbhd_ranges(cell_start, c % G, c / G, A, B);
+            const int ne = state[slot];
+            const unsigned key = __float_as_uint(F4[slot].w);
+            ext[slot * SY_EXTRA + ne] = (unsigned short)(key & ((1u << hpr::kPosBits) - 1u));  // same value from all 8 lanes
+            seq = hpr::RangesPlusList(A, B, ext + slot * SY_EXTRA, ne + 1);
+            self = i; tag = slot;
+            // resume: (SA, SB) is the optimum of everything before the new constraint, which is violated
+            sa = SA[slot]; sb = SB[slot]; p0 = seq.length() - 1;
+          } else self = -1;
+        }
+      };
+      auto finish = [&](bool fin, int gbase, int self, int tag, int status, double sa, double sb) {
+        if (fin && (lane & 7) == 0) {
+          F4[tag].w = 0.f;
+          if (status != hpr::kLpVisible) state[tag] = kHidden;
+          else {
+            SA[tag] = sa; SB[tag] = sb;
+            state[tag] = (unsigned char)(state[tag] + 1);
+            vlist[atomicAdd(&s_nlist, 1)] = (unsigned short)tag;
+          }
+        }
+      };
+      hpr_solve_groups(h, fetch, finish);
+    }
+    __syncthreads();
+    nlist = s_nlist;
+    first = false;
+    __syncthreads();
   }
-  __syncthreads();
-
-  // ---- phase 3: the rare dirty survivors redo the LP over the full sequence (neighbourhood, then all
-  // other points in index order), one warp each; clean survivors are visible.
-  if (tid == 0) s_queue = 0;
-  __syncthreads();
-  while (true) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(&s_queue, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= nsurv) break;
-    const int i = surv[t];
-    if (dirty[i] != 1) { if (lane == 0) flag[i] = 1; continue; }
-    Nbhd nb;
-    make_nbhd(h, i, s_nb[warp], nb);
-    double sa = 0.0, sb = 0.0;
-    const bool vis = hpr_lp_warp(h, nb, i, n, sa, sb);
-    if (lane == 0) flag[i] = vis ? 1 : 0;
-  }
+  if (tid == 0) { tk[4] = clock64(); if (tk[3] == 0) tk[3] = tk[4]; }
+  for (int slot = tid; slot < nsurv; slot += SY_THREADS)
+    if (state[slot] != kHidden) flag[id[surv[slot]]] = 1;
   __syncthreads();
 
   // ---- ordered compaction by ORIGINAL index (visible ids ascending)
@@ -517,25 +661,15 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
   const int i0 = tid * per, i1 = min(n, i0 + per);
   int cnt = 0;
   for (int i = i0; i < i1; ++i) cnt += flag[i];
-  int inc = cnt;
-  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-  if (lane == 31) s_warp_tot[warp] = inc;
-  __syncthreads();  // every thread is past the LP phases: the U region may now be reused for ids[]
-  if (warp == 0) {
-    int v = s_warp_tot[lane], iv = v;
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
-    s_warp_tot[lane] = iv - v;
-    if (lane == 31) s_count = iv;
-  }
-  __syncthreads();
-  int pos = s_warp_tot[warp] + inc - cnt;
+  int nvis_all;
+  int pos = block_excl_scan(cnt, s_warp_tot, nvis_all);   // its barriers also retire the LP phases: Us may be reused
   for (int i = i0; i < i1; ++i) {
     if (flags_out) flags_out[(size_t)cloud * n + i] = flag[i];
     if (flag[i]) ids[pos++] = i;
   }
   __syncthreads();
   // reference quirk: visibleId[:-1] drops the highest-index visible point (hidden_point_removal.py:36)
-  const int nv = max(s_count - 1, 0);
+  const int nv = max(nvis_all - 1, 0);
   if (tid == 0) num_vis[cloud] = nv;
   const float* __restrict__ op = org + (size_t)cloud * org_stride_pts * 3;
   float* __restrict__ dst = out_pts + (size_t)cloud * take * 3;
@@ -549,6 +683,12 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
     dst[r * 3 + 0] = src >= 0 ? op[src * 3 + 0] : 0.f;
     dst[r * 3 + 1] = src >= 0 ? op[src * 3 + 1] : 0.f;
     dst[r * 3 + 2] = src >= 0 ? op[src * 3 + 2] : 0.f;
+  }
+  if (tid == 0) {
+    tk[5] = clock64();
+    long long* g = g_hpr_timing + (blockIdx.x % 512) * 8;
+    for (int k = 0; k < 5; ++k) g[k] = tk[k + 1] - tk[k];
+    g[5] = nsurv; g[6] = dbg_rounds; g[7] = dbg_resolved;
   }
 }
 
@@ -582,14 +722,18 @@ extern "C" int caae_synth_points(int b, int nm, int no, const float* models, con
   return CAAE_LAUNCH_STATUS();
 }
 
+extern "C" int caae_debug_hpr_timing(long long* host_buf) {
+  CAAE_RETURN_IF(!host_buf, CAAE_E_NULLPTR);
+  return (int)cudaMemcpyFromSymbol(host_buf, g_hpr_timing, sizeof(long long) * 512 * 8);
+}
+
 extern "C" int caae_hpr_select(int b, int n, const float* flipped, const float* org, int org_stride_pts, int take,
                                const float* pad_uniform, float* out_pts, int* num_vis, unsigned char* flags_out,
                                caae_stream_t stream) {
   CAAE_RETURN_IF(b < 0 || n <= 0 || n > SY_MAXN || take <= 0 || org_stride_pts < n, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!flipped || !org || !out_pts || !num_vis, CAAE_E_NULLPTR);
-  size_t smem = (size_t)n * (5 * sizeof(double) + sizeof(float4) + 2 * sizeof(unsigned short) + 4) + 8 +
-                sizeof(int) * (2 * SY_G * SY_G + 1) + 16;
+  size_t smem = (size_t)n * SY_BYTES_PER_POINT + 8 + sizeof(int) * (2 * hpr::G * hpr::G + 1) + 16;
   smem = (smem + 15) & ~(size_t)15;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(hpr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -180,13 +180,19 @@ int caae_synth_points(int b, int nm, int no, const float* models, const int* cla
                       float wnear, float near_dist, float flip_pow, float* points, float* flip_all, float* flip_org,
                       caae_stream_t stream);
 
-/* Hidden point removal on flipped f32[b,n,3] (the viewpoint/origin row is implicit) + convexHull()'s
+/* (n <= 2688: one CTA per cloud keeps 82 bytes of shared memory per point.)
+ * Hidden point removal on flipped f32[b,n,3] (the viewpoint/origin row is implicit) + convexHull()'s
  * selection: visible ids ascending, the highest one dropped, first `take` rows of org gathered into
  * out_pts f32[b,take,3], short sets padded by picks pad_uniform f32[b,take] in [0,1) (NULL: cyclic).
  * num_vis i32[b] = visible count after the drop; flags_out u8[b,n] (optional) = hull-vertex flags. */
 int caae_hpr_select(int b, int n, const float* flipped, const float* org, int org_stride_pts, int take,
                     const float* pad_uniform, float* out_pts, int* num_vis, unsigned char* flags_out,
                     caae_stream_t stream);
+
+/* Diagnostics (synchronous): copies the per-CTA phase timing of the LAST caae_hpr_select launch into
+ * host_buf i64[512][8] = clock64 deltas {set-up, neighbourhood LPs, first verification, later rounds,
+ * compaction + selection}, survivors, rounds, slots re-solved in round 0. */
+int caae_debug_hpr_timing(long long* host_buf);
 
 #ifdef __cplusplus
 }
