@@ -71,6 +71,7 @@ _SIGNATURES = {
     "caae_philox_fill": "lpQipi" "p",
     "caae_synth_points": "iiippppppffffppp" "p",
     "caae_hpr_select": "iippiipppp" "p",
+    "caae_hpr_select_pair": "iipipppipippppi" "p",
 }
 _SIGNATURES = {k: [_CODES[c] for c in v] for k, v in _SIGNATURES.items()}
 _SPECIAL = {

@@ -45,22 +45,33 @@ HPR_HD void lift(double x, double y, double z, double rho, double& u, double& v,
   w = -rho * rho / z + 0.5 * rho * (u * u + v * v);
 }
 
-// The 3x3 cell neighbourhood of cell (cx, cy) as three position ranges (cells of one grid row are
-// consecutive in the sorted order): the point's own row first, then the row above, then the row below.
-HPR_HD void nbhd_ranges(const int* cell_start, int cx, int cy, int (&A)[3], int (&B)[3]) {
-  const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx < G - 1 ? cx + 1 : G - 1;
+// Neighbourhood half-width of a cell: 0 (the cell alone) when it is dense enough to hold a point's
+// nearest neighbours by itself, else 1 (the 3x3 block).  Verification covers whatever lies outside.
+#ifndef HPR_DENSE_CELL
+#define HPR_DENSE_CELL 100000  /* measured on B200: shrinking dense cells to k = 0 costs more in verification than it saves */
+#endif
+HPR_HD int nbhd_halfwidth(const int* cell_start, int c) {
+  return (cell_start[c + 1] - cell_start[c] >= HPR_DENSE_CELL) ? 0 : 1;
+}
+
+// The (2k+1)x(2k+1) cell neighbourhood of cell (cx, cy), k in {0, 1}, as three position ranges (cells of
+// one grid row are consecutive in the sorted order): the point's own row first, then the row above, then
+// the row below.
+HPR_HD void nbhd_ranges(const int* cell_start, int cx, int cy, int k, int (&A)[3], int (&B)[3]) {
+  const int x0 = cx - k > 0 ? cx - k : 0, x1 = cx + k < G - 1 ? cx + k : G - 1;
   A[0] = cell_start[cy * G + x0]; B[0] = cell_start[cy * G + x1 + 1];
-  if (cy > 0) { A[1] = cell_start[(cy - 1) * G + x0]; B[1] = cell_start[(cy - 1) * G + x1 + 1]; }
+  if (k > 0 && cy > 0) { A[1] = cell_start[(cy - 1) * G + x0]; B[1] = cell_start[(cy - 1) * G + x1 + 1]; }
   else { A[1] = 0; B[1] = 0; }
-  if (cy < G - 1) { A[2] = cell_start[(cy + 1) * G + x0]; B[2] = cell_start[(cy + 1) * G + x1 + 1]; }
+  if (k > 0 && cy < G - 1) { A[2] = cell_start[(cy + 1) * G + x0]; B[2] = cell_start[(cy + 1) * G + x1 + 1]; }
   else { A[2] = 0; B[2] = 0; }
 }
 
 // Everything outside the neighbourhood, as up to four more ranges (used by the full re-solve).
-HPR_HD void full_ranges(const int (&A)[3], const int (&B)[3], int cy, int n_unique, int (&FA)[7], int (&FB)[7]) {
+HPR_HD void full_ranges(const int (&A)[3], const int (&B)[3], int cy, int k, int n_unique, int (&FA)[7], int (&FB)[7]) {
   for (int r = 0; r < 3; ++r) { FA[r] = A[r]; FB[r] = B[r]; }
-  const int at = cy > 0 ? A[1] : 0, bt = cy > 0 ? B[1] : 0;
-  const int ab = cy < G - 1 ? A[2] : n_unique, bb = cy < G - 1 ? B[2] : n_unique;
+  const bool up = k > 0 && cy > 0, down = k > 0 && cy < G - 1;
+  const int at = up ? A[1] : 0, bt = up ? B[1] : 0;
+  const int ab = down ? A[2] : n_unique, bb = down ? B[2] : n_unique;
   FA[3] = 0; FB[3] = at;            // before the upper row's cells
   FA[4] = bt; FB[4] = A[0];         // between the upper row's cells and the own row's
   FA[5] = B[0]; FB[5] = ab;         // between the own row's and the lower row's

@@ -325,14 +325,31 @@ __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch
   }
 }
 
+// One launch serves up to two independent HPR problems over the same batch (the occluded cloud and the
+// bare object of every sample): 2b CTAs keep all SMs busy where two launches of b <= 148 CTAs would
+// each wait for their slowest cloud.
+struct HprJob {
+  int n, org_stride_pts, take;
+  const float* flipped; const float* org; const float* pad_uniform;
+  float* out_pts; int* num_vis; unsigned char* flags_out;
+};
+struct HprJobs { HprJob job[2]; int b; };
+
 // Diagnostics: per CTA (modulo 512) clock64 deltas {set-up, phase 1, first verification, remaining rounds,
 // compaction+select}, then {survivors, rounds, re-solved in round 0}; read with caae_debug_hpr_timing.
 __device__ long long g_hpr_timing[512 * 8];
 
 __global__ void __launch_bounds__(SY_THREADS)
-hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restrict__ org, int org_stride_pts, int take,
-                  const float* __restrict__ pad_uniform, float* __restrict__ out_pts, int* __restrict__ num_vis,
-                  unsigned char* __restrict__ flags_out) {
+hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
+  // CTA -> (job, cloud): all clouds of job 0 first (the caller puts the larger clouds there), then job 1
+  const HprJob& J = jobs.job[blockIdx.x / jobs.b];
+  const int n = J.n, org_stride_pts = J.org_stride_pts, take = J.take;
+  const float* __restrict__ flipped = J.flipped;
+  const float* __restrict__ org = J.org;
+  const float* __restrict__ pad_uniform = J.pad_uniform;
+  float* __restrict__ out_pts = J.out_pts;
+  int* __restrict__ num_vis = J.num_vis;
+  unsigned char* __restrict__ flags_out = J.flags_out;
   static_assert(hpr::G * hpr::G == SY_THREADS, "one grid cell per thread");
   constexpr int G = hpr::G;
   extern __shared__ __align__(16) unsigned char sy_smem[];
@@ -359,7 +376,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
   __shared__ float s_box[4], s_fzrow[hpr::G], s_fzmax;
   __shared__ int s_count, s_queue, s_nlist, s_nwork;
 
-  const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int cloud = blockIdx.x % jobs.b, tid = threadIdx.x, lane = tid & 31;
   const float* __restrict__ f = flipped + (size_t)cloud * n * 3;
 
   long long tk[6] = {0, 0, 0, 0, 0, 0};
@@ -483,7 +500,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
         if (t < n_unique) {
           const int c = hpr::find_cell(cell_start, t);
           int A[3], B[3];
-          hpr::nbhd_ranges(cell_start, c % G, c / G, A, B);
+          hpr::nbhd_ranges(cell_start, c % G, c / G, hpr::nbhd_halfwidth(cell_start, c), A, B);
           seq = hpr::RangesPlusList(A, B, nullptr, 0);
           self = t; tag = 0;
         } else self = -1;
@@ -535,8 +552,8 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
         const double sa = SA[slot], sb = SB[slot];
         const float saf = (float)sa, sbf = (float)sb;
         const int c = hpr::find_cell(cell_start, i);
-        const int ccx = c % G, ccy = c / G;
-        const int nx0 = max(ccx - 1, 0), nx1 = min(ccx + 1, G - 1);
+        const int ccx = c % G, ccy = c / G, nk = hpr::nbhd_halfwidth(cell_start, c);
+        const int nx0 = max(ccx - nk, 0), nx1 = min(ccx + nk, G - 1);
         const float ctru = fi.x - saf / (2.f * kh), ctrv = fi.y - sbf / (2.f * kh);   // disk centre
         unsigned key = 0;
         bool hidden = false;
@@ -545,7 +562,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
         const int cy0 = max((int)floorf((ctrv - rg - s_box[1]) * gy - 0.01f), 0);
         const int cy1 = min((int)floorf((ctrv + rg - s_box[1]) * gy + 0.01f), G - 1);
         for (int cy = cy0; cy <= cy1; ++cy) {
-          const bool nrow = cy >= ccy - 1 && cy <= ccy + 1;
+          const bool nrow = cy >= ccy - nk && cy <= ccy + nk;
           const float r2 = hpr::verify_disk2(saf, sbf, fi.z, s_fzrow[cy], kh);
           const float lo = s_box[1] + (float)cy * chh, hi = lo + chh;
           const float dv = fmaxf(fmaxf(lo - ctrv, ctrv - hi), 0.f) * 0.999f - 0.01f * chh;  // rounded inwards
@@ -596,8 +613,9 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
         const int i = surv[slot];
         const int c = hpr::find_cell(cell_start, i);
         int A[3], B[3], FA[7], FB[7];
-        hpr::nbhd_ranges(cell_start, c % G, c / G, A, B);
-        hpr::full_ranges(A, B, c / G, n_unique, FA, FB);
+        const int nk = hpr::nbhd_halfwidth(cell_start, c);
+        hpr::nbhd_ranges(cell_start, c % G, c / G, nk, A, B);
+        hpr::full_ranges(A, B, c / G, nk, n_unique, FA, FB);
         double sa, sb;
         if (hpr::lp_lane(h, i, hpr::Ranges<7>(FA, FB), sa, sb) != hpr::kLpVisible) state[slot] = kHidden;
         continue;
@@ -622,7 +640,7 @@ hpr_select_kernel(int n, const float* __restrict__ flipped, const float* __restr
             const int i = surv[slot];
             const int c = hpr::find_cell(cell_start, i);
             int A[3], B[3];
-            hpr::nbhd_ranges(cell_start, c % G, c / G, A, B);
+            hpr::nbhd_ranges(cell_start, c % G, c / G, hpr::nbhd_halfwidth(cell_start, c), A, B);
             const int ne = state[slot];
             const unsigned key = __float_as_uint(F4[slot].w);
             ext[slot * SY_EXTRA + ne] = (unsigned short)(key & ((1u << hpr::kPosBits) - 1u));  // same value from all 8 lanes
@@ -727,20 +745,43 @@ extern "C" int caae_debug_hpr_timing(long long* host_buf) {
   return (int)cudaMemcpyFromSymbol(host_buf, g_hpr_timing, sizeof(long long) * 512 * 8);
 }
 
-extern "C" int caae_hpr_select(int b, int n, const float* flipped, const float* org, int org_stride_pts, int take,
-                               const float* pad_uniform, float* out_pts, int* num_vis, unsigned char* flags_out,
-                               caae_stream_t stream) {
-  CAAE_RETURN_IF(b < 0 || n <= 0 || n > SY_MAXN || take <= 0 || org_stride_pts < n, CAAE_E_BADSHAPE);
-  if (b == 0) return CAAE_OK;
-  CAAE_RETURN_IF(!flipped || !org || !out_pts || !num_vis, CAAE_E_NULLPTR);
-  size_t smem = (size_t)n * SY_BYTES_PER_POINT + 8 + sizeof(int) * (2 * hpr::G * hpr::G + 1) + 16;
+static int hpr_launch(int b, int njobs, const HprJob* jobs, caae_stream_t stream) {
+  HprJobs J;
+  J.b = b;
+  int nmax = 0;
+  for (int k = 0; k < 2; ++k) {
+    J.job[k] = jobs[k < njobs ? k : 0];
+    const HprJob& j = J.job[k];
+    CAAE_RETURN_IF(j.n <= 0 || j.n > SY_MAXN || j.take <= 0 || j.org_stride_pts < j.n, CAAE_E_BADSHAPE);
+    CAAE_RETURN_IF(!j.flipped || !j.org || !j.out_pts || !j.num_vis, CAAE_E_NULLPTR);
+    nmax = j.n > nmax ? j.n : nmax;
+  }
+  size_t smem = (size_t)nmax * SY_BYTES_PER_POINT + 8 + sizeof(int) * (2 * hpr::G * hpr::G + 1) + 16;
   smem = (smem + 15) & ~(size_t)15;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(hpr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  hpr_select_kernel<<<b, SY_THREADS, smem, as_stream(stream)>>>(n, flipped, org, org_stride_pts, take, pad_uniform, out_pts, num_vis,
-                                                                flags_out);
+  hpr_select_kernel<<<b * njobs, SY_THREADS, smem, as_stream(stream)>>>(J);
   return CAAE_LAUNCH_STATUS();
 }
 
+extern "C" int caae_hpr_select(int b, int n, const float* flipped, const float* org, int org_stride_pts, int take,
+                               const float* pad_uniform, float* out_pts, int* num_vis, unsigned char* flags_out,
+                               caae_stream_t stream) {
+  CAAE_RETURN_IF(b < 0, CAAE_E_BADSHAPE);
+  if (b == 0) return CAAE_OK;
+  const HprJob job = {n, org_stride_pts, take, flipped, org, pad_uniform, out_pts, num_vis, flags_out};
+  return hpr_launch(b, 1, &job, stream);
+}
+
+extern "C" int caae_hpr_select_pair(int b, int n_a, const float* flipped_a, int take_a, const float* pad_uniform_a,
+                                    float* out_pts_a, int* num_vis_a, int n_b, const float* flipped_b, int take_b,
+                                    const float* pad_uniform_b, float* out_pts_b, int* num_vis_b, const float* org,
+                                    int org_stride_pts, caae_stream_t stream) {
+  CAAE_RETURN_IF(b < 0, CAAE_E_BADSHAPE);
+  if (b == 0) return CAAE_OK;
+  const HprJob jobs[2] = {{n_a, org_stride_pts, take_a, flipped_a, org, pad_uniform_a, out_pts_a, num_vis_a, nullptr},
+                          {n_b, org_stride_pts, take_b, flipped_b, org, pad_uniform_b, out_pts_b, num_vis_b, nullptr}};
+  return hpr_launch(b, 2, jobs, stream);
+}

@@ -97,10 +97,11 @@ class SegmentSynthesizer:
         self._c("caae_synth_points", B, self.nm, self.no, p(self.models), p(class_id), p(axisangle), p(translation),
                 p(self.z_centers), p(self.z_points), self.hnear, self.wnear, self.near, self.flip_pow, p(self.points),
                 p(self.flip_all), p(self.flip_org))
-        self._c("caae_hpr_select", B, n, p(self.flip_all), p(self.points), n, self.N, p(self.pad_u), p(self.visible),
-                p(self.num_vis), None)
-        self._c("caae_hpr_select", B, self.nm, p(self.flip_org), p(self.points), n, 4 * self.N, p(self.pad_u_org),
-                p(self.target), p(self.num_vis_org), None)
+        # both hidden-point-removal problems (occluded cloud -> network input, bare object -> chamfer target)
+        # in one launch of 2B CTAs
+        self._c("caae_hpr_select_pair", B, n, p(self.flip_all), self.N, p(self.pad_u), p(self.visible), p(self.num_vis),
+                self.nm, p(self.flip_org), 4 * self.N, p(self.pad_u_org), p(self.target), p(self.num_vis_org),
+                p(self.points), n)
         return self.visible, self.target, self.noise
 
 

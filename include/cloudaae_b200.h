@@ -189,6 +189,15 @@ int caae_hpr_select(int b, int n, const float* flipped, const float* org, int or
                     const float* pad_uniform, float* out_pts, int* num_vis, unsigned char* flags_out,
                     caae_stream_t stream);
 
+/* The training step's two HPR problems over one batch in ONE launch of 2b CTAs: (a) the occluded cloud
+ * flipped_a f32[b,n_a,3] -> first take_a visible points (the network input, train_cloudAAE_ycbv.py:213)
+ * and (b) the bare object flipped_b f32[b,n_b,3] -> first take_b visible points (the chamfer target,
+ * :214).  Both gather from org f32[b,org_stride_pts,3].  Same results as two caae_hpr_select calls. */
+int caae_hpr_select_pair(int b, int n_a, const float* flipped_a, int take_a, const float* pad_uniform_a,
+                         float* out_pts_a, int* num_vis_a, int n_b, const float* flipped_b, int take_b,
+                         const float* pad_uniform_b, float* out_pts_b, int* num_vis_b, const float* org,
+                         int org_stride_pts, caae_stream_t stream);
+
 /* Diagnostics (synchronous): copies the per-CTA phase timing of the LAST caae_hpr_select launch into
  * host_buf i64[512][8] = clock64 deltas {set-up, neighbourhood LPs, first verification, later rounds,
  * compaction + selection}, survivors, rounds, slots re-solved in round 0. */

@@ -85,7 +85,8 @@ extern "C" int hpr_host_iters(const float* flipped, int b, int n, unsigned char*
     for (int p = 0; p < nu; ++p) {
       const int cx = cell_of[p] % G, cy = cell_of[p] / G;
       int A[3], B[3];
-      nbhd_ranges(cell_start.data(), cx, cy, A, B);
+      const int kk = nbhd_halfwidth(cell_start.data(), cell_of[p]);
+      nbhd_ranges(cell_start.data(), cx, cy, kk, A, B);
       double sa, sb;
       int it = 0;
       static const int scatter = std::getenv("HPR_SCATTER") ? std::atoi(std::getenv("HPR_SCATTER")) : 0;
@@ -135,7 +136,7 @@ extern "C" int hpr_host_iters(const float* flipped, int b, int n, unsigned char*
         ++rounds;
         if (nextra == kExtra) {  // rare: the full LP (neighbourhood first, then everything else)
           int FA[7], FB[7];
-          full_ranges(A, B, cy, nu, FA, FB);
+          full_ranges(A, B, cy, kk, nu, FA, FB);
           vis = lp_lane(h, p, Ranges<7>(FA, FB), sa, sb, 0, &it) == kLpVisible;
           st[4] += it;
           break;

@@ -31,3 +31,9 @@ for name, args in (("hpr occluded", (B, n, p(syn.flip_all), p(syn.points), n, sy
     e.record(); torch.cuda.synchronize()
     print("%s ms: %.3f" % (name, s.elapsed_time(e) / 20))
 print("num_vis mean", syn.num_vis.float().mean().item(), "org", syn.num_vis_org.float().mean().item())
+s.record()
+for i in range(20):
+    lib.caae_hpr_select_pair(B, n, p(syn.flip_all), syn.N, p(syn.pad_u), p(syn.visible), p(syn.num_vis), syn.nm, p(syn.flip_org),
+                             4 * syn.N, p(syn.pad_u_org), p(syn.target), p(syn.num_vis_org), p(syn.points), n, st)
+e.record(); torch.cuda.synchronize()
+print("hpr pair ms: %.3f" % (s.elapsed_time(e) / 20))
