@@ -80,10 +80,21 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
   }
 
   const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
+  // split-K partial tiles: one 16-byte vector reduction per four outputs (red.global.add.v4.f32, sm_90+)
+  // instead of four scalar atomics — the L2 atomic units were the bottleneck of the skinny FC GEMMs
+  const bool vec_ok = use_atomics && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0) &&
+                      (n0 + tx * 4 + 3 < N);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int gm = m0 + ty * 8 + i;
     if (gm >= M) continue;
+    if (vec_ok) {
+      const int gn = n0 + tx * 4;
+      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (add_bias) { v.x += __ldg(bias + gn); v.y += __ldg(bias + gn + 1); v.z += __ldg(bias + gn + 2); v.w += __ldg(bias + gn + 3); }
+      atomicAdd(reinterpret_cast<float4*>(C + (size_t)gm * ldc + gn), v);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;

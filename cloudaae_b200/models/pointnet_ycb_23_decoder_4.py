@@ -224,7 +224,8 @@ class _Engine:
         weight-bandwidth bound, and its batch-norm backward over only `batch` rows amplifies TF32
         rounding of the pre-activations far beyond the 1e-3 parity budget."""
         fn = "caae_gemm_f32"
-        if (self.precision == "tf32" and M * N * K >= (1 << 29) and
+        # (N < 128 would leave half of the kernel's 128 x 128 tile idle: measured slower than the FFMA kernel)
+        if (self.precision == "tf32" and M * N * K >= (1 << 29) and N >= 128 and
                 self.lib.caae_gemm_tf32_supported(ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb)):
             fn = "caae_gemm_tf32"
         self._c(fn, ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), acc)
