@@ -38,8 +38,11 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = kbeg; k0 < kend; k0 += GBK) {
-    // ---- stage A tile (GBM x GBK) as As[k][m]
+  // Software pipeline: the global loads of K-step s+1 are issued into registers before the FFMA block
+  // of step s, so their latency overlaps the arithmetic (the skinny FC GEMMs run one or two CTAs per
+  // SM with a handful of K-steps each: nothing else would hide it).
+  float ra[(GBM * GBK) / GTHREADS], rb[(GBK * GBN) / GTHREADS];
+  auto gload = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < (GBM * GBK) / GTHREADS; ++i) {
       const int e = tid + i * GTHREADS;
@@ -49,9 +52,8 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.f;
       if (gm < M && gk < kend) v = TA ? __ldg(A + (size_t)gk * lda + gm) : __ldg(A + (size_t)gm * lda + gk);
-      As[k][m] = v;
+      ra[i] = v;
     }
-    // ---- stage B tile (GBK x GBN) as Bs[k][n]
 #pragma unroll
     for (int i = 0; i < (GBK * GBN) / GTHREADS; ++i) {
       const int e = tid + i * GTHREADS;
@@ -61,9 +63,26 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
       const int gn = n0 + n, gk = k0 + k;
       float v = 0.f;
       if (gn < N && gk < kend) v = TB ? __ldg(B + (size_t)gn * ldb + gk) : __ldg(B + (size_t)gk * ldb + gn);
-      Bs[k][n] = v;
+      rb[i] = v;
     }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int i = 0; i < (GBM * GBK) / GTHREADS; ++i) {
+      const int e = tid + i * GTHREADS;
+      if (TA) As[e / GBM][e % GBM] = ra[i]; else As[e % GBK][e / GBK] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < (GBK * GBN) / GTHREADS; ++i) {
+      const int e = tid + i * GTHREADS;
+      if (TB) Bs[e % GBK][e / GBK] = rb[i]; else Bs[e / GBN][e % GBN] = rb[i];
+    }
+  };
+  if (kbeg < kend) gload(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+    sstore();
     __syncthreads();
+    if (k0 + GBK < kend) gload(k0 + GBK);
 #pragma unroll
     for (int k = 0; k < GBK; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);

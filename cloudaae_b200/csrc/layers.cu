@@ -337,16 +337,6 @@ bn_act_bwd_kernel(long total, int C, const float* Y, int ld, const float* __rest
   }
 }
 
-// out[c] = sum_r X[r][c]  (bias gradients of the linear output layers; R is the batch)
-__global__ void __launch_bounds__(256)
-colsum_kernel(int R, int C, const float* __restrict__ X, int ld, float* __restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= C) return;
-  float s = 0.f;
-  for (int r = 0; r < R; ++r) s += X[(size_t)r * ld + ch];
-  out[ch] = s;
-}
-
 // EdgeConv weight factorisation: W [2c, cout] -> Wf [c, 2cout] = [W_top - W_bot | W_bot], bias_f = [bias | 0]
 __global__ void edge_fold_weights_kernel(int c, int cout, const float* __restrict__ w, int ldw,
                                          const float* __restrict__ bias, float* __restrict__ wf,
@@ -790,13 +780,6 @@ extern "C" int caae_bn_act_bwd_apply(int R, int C, const float* Y, int ld, const
   bn_act_bwd_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(total, C, Y, ld, scale, shift, mean, invstd,
                                                                        coef, dOut, lddo, group, gscale, relu, argmax,
                                                                        dY, lddy);
-  return CAAE_LAUNCH_STATUS();
-}
-
-extern "C" int caae_colsum(int R, int C, const float* X, int ld, float* out, caae_stream_t stream) {
-  CAAE_RETURN_IF(R < 0 || C <= 0 || ld < C, CAAE_E_BADSHAPE);
-  CAAE_RETURN_IF(!X || !out, CAAE_E_NULLPTR);
-  colsum_kernel<<<(C + 255) / 256, 256, 0, as_stream(stream)>>>(R, C, X, ld, out);
   return CAAE_LAUNCH_STATUS();
 }
 

@@ -487,9 +487,29 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
   h.U = Us; h.V = Vs; h.W = Ws; h.id = id; h.cell_start = cell_start; h.kappa = rho; h.n_unique = n_unique;
 
   if (tid == 0) tk[1] = clock64();
-  // ---- phase 1: incremental LP of every point over its 3x3 cell neighbourhood (own grid row first),
-  // eight lanes per point, points handed out in sorted order from a queue.  Survivors (~40 %) are
+  // ---- visible-prefix mode.  The caller consumes only the first `take` visible points in index order
+  // (the training graph slices vis[:, :num_point], train_cloudAAE_ycbv.py:213-214), so only points up to
+  // the index where take + 1 visible ones are known need an LP of their own (the +1: the reference drops
+  // the highest visible index, hidden_point_removal.py:36).  Every point still acts as a CONSTRAINT of
+  // those LPs.  Indices are handed out in growing windows [lo, hi) until enough are found; the object
+  // models are stored in farthest-point order, so ~3 take indices usually suffice and the dense
+  // occluder blobs at the end of the cloud are never solved for.
+  const bool prefix = flags_out == nullptr && take + 1 < n;
+  int lo = 0, hi = prefix ? min(n, 3 * take) : n;
+  int slot_base = 0, nsurv = 0;
+  const float kh = 0.5f * (float)rho;
+  while (true) {
+  // ---- phase 1: incremental LP of every point of the window over its 3x3 cell neighbourhood (own grid
+  // row first), eight lanes per point, points handed out from a work list.  Survivors (~40 %) are
   // recorded with their optimum.
+  if (tid == 0) { s_nwork = 0; s_queue = 0; }
+  __syncthreads();
+  for (int p = tid; p < n_unique; p += SY_THREADS) {
+    const int i = id[p];
+    if (i >= lo && i < hi) wlist[atomicAdd(&s_nwork, 1)] = (unsigned short)p;
+  }
+  __syncthreads();
+  const int nwork1 = s_nwork;
   {
     auto fetch = [&](bool want, int gbase, int& self, hpr::RangesPlusList& seq, int& tag, double& sa, double& sb, int& p0) {
       int t = 0;
@@ -497,12 +517,13 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
       t = __shfl_sync(0xffffffffu, t, gbase);
       if (want) {
         sa = 0.0; sb = 0.0; p0 = 0;
-        if (t < n_unique) {
-          const int c = hpr::find_cell(cell_start, t);
+        if (t < nwork1) {
+          const int pos = wlist[t];
+          const int c = hpr::find_cell(cell_start, pos);
           int A[3], B[3];
           hpr::nbhd_ranges(cell_start, c % G, c / G, hpr::nbhd_halfwidth(cell_start, c), A, B);
           seq = hpr::RangesPlusList(A, B, nullptr, 0);
-          self = t; tag = 0;
+          self = pos; tag = 0;
         } else self = -1;
       }
     };
@@ -517,7 +538,6 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
     hpr_solve_groups(h, fetch, finish);
   }
   __syncthreads();
-
   // ---- phases 2 / 3, in rounds.  Verify: every listed survivor's optimum against all points, as
   // (survivor, 256-position slice) work items; lanes of a warp share the slice (broadcast LDS.128 of the
   // fp32 copy); a conservative fp32 evaluation dismisses constraints that are clearly slack, the few
@@ -525,10 +545,9 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
   // slot's key.  Re-solve: one thread per violated survivor adds that constraint to its LP (neighbourhood
   // + added constraints) and solves it again; it is verified again in the next round.  A survivor is
   // visible once a verification finds nothing.
-  if (tid == 0) tk[2] = clock64();
-  const int nsurv = s_count;
-  const float kh = 0.5f * (float)rho;
-  int nlist = nsurv;   // round 0 verifies every survivor (list = identity)
+  if (tid == 0 && lo == 0) tk[2] = clock64();
+  nsurv = s_count;
+  int nlist = nsurv - slot_base;   // round 0 verifies every new survivor (list = identity)
   bool first = true;
   while (nlist > 0) {
     if (tid == 0) { s_nwork = 0; s_queue = 0; s_nlist = 0; }
@@ -544,7 +563,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
       const float gx = (float)G / s_box[2], gy = (float)G / s_box[3];
       const float chh = s_box[3] / (float)G;   // cell height
       for (int li = tid >> 3; li < nlist; li += SY_THREADS / 8) {
-        const int slot = first ? li : (int)vlist[li];
+        const int slot = first ? slot_base + li : (int)vlist[li];
         const int ne = state[slot];
         if (ne == kHidden) continue;
         const int i = surv[slot];
@@ -606,7 +625,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
     __syncthreads();
     // ---- the listed slots whose key is set go to the work list (hidden / verified-clean ones drop out)
     for (int li = tid; li < nlist; li += SY_THREADS) {
-      const int slot = first ? li : (int)vlist[li];
+      const int slot = first ? slot_base + li : (int)vlist[li];
       const int ne = state[slot];
       if (ne == kHidden || __float_as_uint(F4[slot].w) == 0u) continue;
       if (ne == SY_EXTRA) {   // constraint list full (never seen on the fixtures): the full LP settles it
@@ -624,7 +643,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
     }
     __syncthreads();
     const int nwork = s_nwork;
-    if (tid == 0 && first) { tk[3] = clock64(); dbg_resolved = nwork; }
+    if (tid == 0 && first && lo == 0) { tk[3] = clock64(); dbg_resolved = nwork; }
     ++dbg_rounds;
     // ---- re-solve: the worst violator joins the slot's constraint list and the incremental LP takes
     // that one more step (clip its boundary line against neighbourhood + list); slots that stay feasible
@@ -669,10 +688,20 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
     first = false;
     __syncthreads();
   }
-  if (tid == 0) { tk[4] = clock64(); if (tk[3] == 0) tk[3] = tk[4]; }
-  for (int slot = tid; slot < nsurv; slot += SY_THREADS)
+  for (int slot = slot_base + tid; slot < nsurv; slot += SY_THREADS)
     if (state[slot] != kHidden) flag[id[surv[slot]]] = 1;
   __syncthreads();
+  if (hi >= n) break;
+  {  // enough visible points known?
+    int c = 0;
+    for (int i = tid; i < hi; i += SY_THREADS) c += flag[i];
+    int vis_known;
+    block_excl_scan(c, s_warp_tot, vis_known);
+    if (vis_known >= take + 1) break;
+  }
+  slot_base = nsurv; lo = hi; hi = min(n, hi + 2 * take);
+  }
+  if (tid == 0) { tk[4] = clock64(); if (tk[3] == 0) tk[3] = tk[4]; }
 
   // ---- ordered compaction by ORIGINAL index (visible ids ascending)
   const int per = (n + SY_THREADS - 1) / SY_THREADS;

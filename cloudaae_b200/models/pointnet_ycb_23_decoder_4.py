@@ -12,6 +12,7 @@ in ONE flat fp32 buffer — the operand of the fused Adam kernel and of the data
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 from collections import OrderedDict
@@ -175,10 +176,10 @@ class _Engine:
             self.d_hcat = torch.empty(R, 320, **f32)
             self.idx = [torch.empty(R, k, dtype=torch.int32, device=self.dev) for _ in range(4)]
             self.pq = [torch.empty(R, 2 * c, **f32) for c in self.couts]
-            self.d_pq = torch.empty(R, 2 * max(self.couts), **f32)
+            self.d_pq = [torch.empty(R, 2 * c, **f32) for c in self.couts]   # per layer: wgrad of layer l overlaps layer l-1
             self.wf = [torch.empty(ci, 2 * co, **f32) for ci, co in zip(self.cins, self.couts)]
             self.bf = [torch.empty(2 * co, **f32) for co in self.couts]
-            self.d_wf = torch.empty(max(self.cins), 2 * max(self.couts), **f32)
+            self.d_wf = [torch.empty(ci, 2 * co, **f32) for ci, co in zip(self.cins, self.couts)]
             self.yagg = torch.empty(R, 1024, **f32)
         else:
             self.enc = ["pn_conv1_encoder", "pn_conv2_encoder", "pn_conv3_encoder", "pn_conv4_encoder",
@@ -204,6 +205,16 @@ class _Engine:
         self.x0 = None
         self.trained = (False, False)
         self.after_fc_backward = None
+        # Independent kernel chains run on forked side streams (and become parallel branches of the
+        # captured CUDA graph): the three FC branches, weight gradients next to the data-gradient chain,
+        # the EdgeConv projection next to the kNN search of the same layer.  Every launch of those chains
+        # is far too small to fill 148 SMs on its own.  CLOUDAAE_STREAMS=0 serialises everything.
+        self.concurrent = os.environ.get("CLOUDAAE_STREAMS", "1") != "0" and self.dev.type == "cuda"
+        self.s_branch = [torch.cuda.Stream(self.dev) for _ in range(2)] if self.concurrent else []
+        self.s_wgrad = [torch.cuda.Stream(self.dev) for _ in range(3)] if self.concurrent else []
+        self.s_enc = torch.cuda.Stream(self.dev) if self.concurrent else None
+        self.d_emb_br = torch.empty(3, B, 1024, **f32)
+        self._heads_pending = False
 
     # -- helpers
     def _st(self):
@@ -215,6 +226,84 @@ class _Engine:
     @staticmethod
     def _p(t):
         return None if t is None else t.data_ptr()
+
+    def _fork(self, s):
+        """Stream `s` continues from everything issued so far on the current stream."""
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+
+    def _join(self, s):
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+
+    def _on(self, s):
+        return torch.cuda.stream(s) if s is not None else contextlib.nullcontext()
+
+    def _fc_fwd(self, scope, x, training, decay):
+        """One fully connected layer on [B, fin]: y = x W + b, then training-mode BN + ReLU in one launch
+        (tf_util.fully_connected, :321-365)."""
+        fin, fout, has_bn = self.scopes[scope]
+        B, v = self.B, self.v
+        y = self.fc_y[scope]
+        self._gemm(0, 0, B, fout, fin, x, fin, v[f"{scope}/weights"], fout, y, fout, v[f"{scope}/biases"])
+        if not has_bn:
+            return None
+        bn, a = self.bn[scope], self.fc_a[scope]
+        if training:
+            self._c("caae_fc_bn_fwd", B, fout, self._p(y), fout, self._p(v[f"{scope}/bn/gamma"]),
+                    self._p(v[f"{scope}/bn/beta"]), self._p(v[f"{scope}/bn/ema_mean"]), self._p(v[f"{scope}/bn/ema_var"]),
+                    self._p(decay), self._p(bn["scale"]), self._p(bn["shift"]), self._p(bn["mean"]),
+                    self._p(bn["invstd"]), 1, self._p(a), fout)
+        else:
+            self._bn_coeffs(scope, False, 1, B, decay)
+            self._c("caae_bn_act", B, fout, self._p(y), fout, self._p(bn["scale"]), self._p(bn["shift"]), 1,
+                    self._p(a), fout)
+        return a
+
+    def _fc_bn_bwd(self, scope, d):
+        """BN + ReLU backward of an FC layer, in place over d [B, fout]; bn/gamma, bn/beta gradients."""
+        C = self.scopes[scope][1]
+        bn, v = self.bn[scope], self.v
+        self._c("caae_fc_bn_bwd", self.B, C, self._p(self.fc_y[scope]), C, self._p(bn["scale"]), self._p(bn["shift"]),
+                self._p(bn["mean"]), self._p(bn["invstd"]), self._p(v[f"{scope}/bn/gamma"]), 1, self._p(d), C,
+                self._p(d), C, self._p(v.grad_of(f"{scope}/bn/gamma")), self._p(v.grad_of(f"{scope}/bn/beta")))
+
+    def _branch_backward(self, bi, d_out):
+        """Backward of FC branch `bi` on the current stream; its weight gradients on their own stream.
+        Leaves d(embedding) of the branch in d_emb_br[bi]."""
+        B = self.B
+        s3, s2, s1 = self.branches[bi][2], self.branches[bi][1], self.branches[bi][0]
+        f3, f2, f1 = self.scopes[s3], self.scopes[s2], self.scopes[s1]
+        w = self.s_wgrad[bi] if self.concurrent else None
+        d_out = d_out.contiguous()
+        d2, d1 = self.fc_d[s2], self.fc_d[s1]
+        # linear output layer
+        if w is not None: self._fork(w)
+        with self._on(w):
+            self._dense_wgrad(s3, self.fc_a[s2], f3[0], B, d_out, True)
+        self._gemm(0, 1, B, f3[0], f3[1], d_out, f3[1], self.v[f"{s3}/weights"], f3[1], d2, f3[0])
+        # fc2: BN+ReLU backward, wgrad, dgrad
+        self._fc_bn_bwd(s2, d2)
+        if w is not None: self._fork(w)
+        with self._on(w):
+            self._dense_wgrad(s2, self.fc_a[s1], f2[0], B, d2, False)
+        self._gemm(0, 1, B, f2[0], f2[1], d2, f2[1], self.v[f"{s2}/weights"], f2[1], d1, f2[0])
+        # fc1
+        self._fc_bn_bwd(s1, d1)
+        if w is not None: self._fork(w)
+        with self._on(w):
+            self._dense_wgrad(s1, self.emb, f1[0], B, d1, False)
+        self._gemm(0, 1, B, f1[0], f1[1], d1, f1[1], self.v[f"{s1}/weights"], f1[1], self.d_emb_br[bi], f1[0])
+        if w is not None: self._join(w)
+
+    def backward_heads_async(self, d_rot, d_trans):
+        """Start the backward pass of the two pose heads (on side streams when enabled): their loss
+        gradients exist long before the chamfer gradient of the decoder branch.  `backward` joins them."""
+        assert self.trained == (True, True), "backward is defined for training-mode batch norm"
+        for bi, d in ((1, d_rot), (2, d_trans)):
+            s = self.s_branch[bi - 1] if self.concurrent else None
+            if s is not None: self._fork(s)
+            with self._on(s):
+                self._branch_backward(bi, d)
+        self._heads_pending = True
 
     def _gemm(self, ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, acc=0):
         """Dense contraction.  precision 'tf32': the tcgen05 tensor-core kernel (TF32 multiply, fp32
@@ -287,13 +376,21 @@ class _Engine:
         before = None
         if self.model == "dgcnn":
             feat, ldf, cknn = x, D, 3
+            se = self.s_enc
+            if se is not None: self._fork(se)
+            with self._on(se):   # the folded weights depend on the parameters only
+                for l in range(4):
+                    self._c("caae_edge_fold_weights", self.cins[l], self.couts[l], self._p(self.v[f"dgcnn{l + 1}/weights"]),
+                            self._p(self.v[f"dgcnn{l + 1}/biases"]), self._p(self.wf[l]), self._p(self.bf[l]), self.couts[l])
             for l in range(4):
                 scope = f"dgcnn{l + 1}"
                 ci, co = self.cins[l], self.couts[l]
+                # the projection [P|Q] = X Wf and the kNN search read the same features: run them side by side
+                if se is not None: self._fork(se)
+                with self._on(se):
+                    self._gemm(0, 0, R, 2 * co, ci, feat, ldf, self.wf[l], 2 * co, self.pq[l], 2 * co, self.bf[l])
                 self._c("caae_knn", B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
-                self._c("caae_edge_fold_weights", ci, co, self._p(self.v[f"{scope}/weights"]),
-                        self._p(self.v[f"{scope}/biases"]), self._p(self.wf[l]), self._p(self.bf[l]), co)
-                self._gemm(0, 0, R, 2 * co, ci, feat, ldf, self.wf[l], 2 * co, self.pq[l], 2 * co, self.bf[l])
+                if se is not None: self._join(se)
                 if train_enc:
                     self._c("caae_edge_stats", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
                             self._p(self.parts))
@@ -323,13 +420,16 @@ class _Engine:
             self._c("caae_bn_act_pool", B, N, 1024, self._p(self.enc_y[-1]), 1024, self._p(bn["scale"]),
                     self._p(bn["shift"]), 1, self._p(self.emb), self._p(self.argmax))
         outs = []
-        for br in self.branches:
-            inp = self.emb
-            for s in br:
-                fin, fout, has_bn = self.scopes[s]
-                self._dense_fwd(s, inp, fin, B, train_fc, decay, self.fc_y[s], self.fc_a.get(s))
-                inp = self.fc_a.get(s)
-            outs.append(self.fc_y[br[-1]])
+        for bi in (1, 2, 0):   # heads on side streams, the decoder on the caller's
+            st = self.s_branch[bi - 1] if (self.concurrent and bi > 0) else None
+            if st is not None: self._fork(st)
+            with self._on(st):
+                inp = self.emb
+                for s in self.branches[bi]:
+                    inp = self._fc_fwd(s, inp, train_fc, decay)
+        for st in self.s_branch:
+            self._join(st)
+        outs = [self.fc_y[br[-1]] for br in self.branches]
         return outs[0], outs[1], outs[2], self.emb, before
 
     # -- backward (training-mode BN only, like the reference's training graph)
@@ -337,24 +437,14 @@ class _Engine:
         """Gradients of all trainable variables into ``variables.grad``.  d_* are f32 [B, fout]."""
         assert self.trained == (True, True), "backward is defined for training-mode batch norm"
         B, N, R, k = self.B, self.N, self.R, self.k
-        first = True
-        for br, d_out in zip(self.branches, (d_recon, d_rot, d_trans)):
-            s3, s2, s1 = br[2], br[1], br[0]
-            f3, f2, f1 = self.scopes[s3], self.scopes[s2], self.scopes[s1]
-            d_out = d_out.contiguous()
-            # linear output layer
-            self._dense_wgrad(s3, self.fc_a[s2], f3[0], B, d_out, True)
-            self._gemm(0, 1, B, f3[0], f3[1], d_out, f3[1], self.v[f"{s3}/weights"], f3[1], self.fc_d[s2], f3[0])
-            # fc2: BN+ReLU backward, wgrad, dgrad
-            self._bn_bwd(s2, B, self.fc_y[s2], self.fc_d[s2], f2[1], 1, 1.0, None, self.fc_d[s2])
-            self._dense_wgrad(s2, self.fc_a[s1], f2[0], B, self.fc_d[s2], False)
-            self._gemm(0, 1, B, f2[0], f2[1], self.fc_d[s2], f2[1], self.v[f"{s2}/weights"], f2[1], self.fc_d[s1], f2[0])
-            # fc1
-            self._bn_bwd(s1, B, self.fc_y[s1], self.fc_d[s1], f1[1], 1, 1.0, None, self.fc_d[s1])
-            self._dense_wgrad(s1, self.emb, f1[0], B, self.fc_d[s1], False)
-            self._gemm(0, 1, B, f1[0], f1[1], self.fc_d[s1], f1[1], self.v[f"{s1}/weights"], f1[1], self.d_emb, f1[0],
-                       None, 0 if first else 1)
-            first = False
+        if not self._heads_pending:
+            self.backward_heads_async(d_rot, d_trans)
+        self._heads_pending = False
+        self._branch_backward(0, d_recon)
+        for st in self.s_branch:
+            self._join(st)
+        self._c("caae_add3", B * 1024, self._p(self.d_emb_br[0]), self._p(self.d_emb_br[1]), self._p(self.d_emb_br[2]),
+                self._p(self.d_emb))
         if d_emb_extra is not None:
             self.d_emb.add_(d_emb_extra)
         if self.after_fc_backward is not None:  # every FC / head gradient is final: start its allreduce
@@ -363,7 +453,10 @@ class _Engine:
             scope = "dgcnn_agg"
             # mean-pool + ReLU + BN backward, in place over the pre-activation
             self._bn_bwd(scope, R, self.yagg, self.d_emb, 1024, N, 1.0 / N, None, self.yagg)
-            self._dense_wgrad(scope, self.hcat, 320, R, self.yagg, False)
+            se = self.s_enc   # weight gradients next to the data-gradient chain
+            if se is not None: self._fork(se)
+            with self._on(se):
+                self._dense_wgrad(scope, self.hcat, 320, R, self.yagg, False)
             self._gemm(0, 1, R, 320, 1024, self.yagg, 1024, self.v[f"{scope}/weights"], 1024, self.d_hcat, 320)
             for l in (3, 2, 1, 0):
                 scope = f"dgcnn{l + 1}"
@@ -376,16 +469,19 @@ class _Engine:
                 self._c("caae_bn_bwd_finalize", co, self._p(self.parts), self.lib.caae_edge_parts(B, N, k, co, 2 * co), float(R * k),
                         self._p(self.v[f"{scope}/bn/gamma"]), self._p(bn["invstd"]), self._p(bn["coef"]),
                         self._p(self.v.grad_of(f"{scope}/bn/gamma")), self._p(self.v.grad_of(f"{scope}/bn/beta")))
-                self._c("caae_edge_bwd_apply", *args, self._p(bn["coef"]), self._p(d_out), 320, self._p(self.d_pq),
-                        2 * co)
+                d_pq, d_wf = self.d_pq[l], self.d_wf[l]
+                self._c("caae_edge_bwd_apply", *args, self._p(bn["coef"]), self._p(d_out), 320, self._p(d_pq), 2 * co)
                 feat, ldf = (self.x0, self.D) if l == 0 else (self.hcat[:, self.offs[l - 1]:], 320)
                 # dWf = X^T dPQ, then unfold to the reference's [2C, cout] weight
-                self._gemm(1, 0, ci, 2 * co, R, feat, ldf, self.d_pq, 2 * co, self.d_wf, 2 * co)
-                self._c("caae_edge_unfold_wgrad", ci, co, self._p(self.d_wf), 2 * co,
-                        self._p(self.v.grad_of(f"{scope}/weights")))
+                if se is not None: self._fork(se)
+                with self._on(se):
+                    self._gemm(1, 0, ci, 2 * co, R, feat, ldf, d_pq, 2 * co, d_wf, 2 * co)
+                    self._c("caae_edge_unfold_wgrad", ci, co, self._p(d_wf), 2 * co,
+                            self._p(self.v.grad_of(f"{scope}/weights")))
                 if l > 0:  # d(net_{l-1}) += dPQ Wf^T, accumulated into its slice of d_hcat
-                    self._gemm(0, 1, R, ci, 2 * co, self.d_pq, 2 * co, self.wf[l], 2 * co,
+                    self._gemm(0, 1, R, ci, 2 * co, d_pq, 2 * co, self.wf[l], 2 * co,
                                self.d_hcat[:, self.offs[l - 1]:], 320, None, 1)
+            if se is not None: self._join(se)
         else:
             last = len(self.enc) - 1
             scope = self.enc[last]

@@ -76,8 +76,10 @@ class CloudAAETrainer:
     def _c(self, name, *args):
         _capi.check(getattr(self.lib, name)(*args, self._st()), name)
 
-    def forward_losses(self, visible, target, class_id, translation, axisangle, noise):
-        """Forward pass + losses (+ the loss gradients w.r.t. the network outputs)."""
+    def forward_losses(self, visible, target, class_id, translation, axisangle, noise, start_heads_backward=False):
+        """Forward pass + losses (+ the loss gradients w.r.t. the network outputs).  start_heads_backward:
+        launch the pose heads' backward pass as soon as their loss gradients exist (side streams), so it
+        overlaps the chamfer forward/backward of the decoder branch; `backward` must follow."""
         B, N, M = self.B, self.N, self.M
         p = _Engine._p
         assert visible.is_contiguous() and target.is_contiguous() and target.shape == (B, M, 3)
@@ -85,11 +87,13 @@ class CloudAAETrainer:
         self._c("caae_prepare_input", B, N, visible.shape[1], p(visible), p(noise), p(class_id), NUM_CLASS, p(self.x),
                 p(self.mean))
         recon, rot, trans, _, _ = self.engine.forward(self.x, True, True, self.decay)
+        self._c("caae_pose_losses", B, p(rot), p(axisangle), p(trans), p(self.mean), p(translation), 1.0 / B, 10.0 / B,
+                p(self.per_rot), p(self.per_trans), p(self.d_rot), p(self.d_trans), p(self.trans_pred))
+        if start_heads_backward:
+            self.engine.backward_heads_async(self.d_rot, self.d_trans)
         self._c("caae_add_cloud_vec", B, M, p(recon), p(self.mean), p(self.recon))
         self._c("caae_nn_distance", B, M, p(self.recon), M, p(target), p(self.dist1), p(self.idx1), p(self.dist2),
                 p(self.idx2))
-        self._c("caae_pose_losses", B, p(rot), p(axisangle), p(trans), p(self.mean), p(translation), 1.0 / B, 10.0 / B,
-                p(self.per_rot), p(self.per_trans), p(self.d_rot), p(self.d_trans), p(self.trans_pred))
         self._c("caae_loss_reduce", B * M, p(self.dist1), p(self.dist2), B, p(self.per_trans), p(self.per_rot),
                 p(self.losses))
         return self.losses
@@ -115,7 +119,7 @@ class CloudAAETrainer:
         translation/axisangle f32[B,3] (labels), noise f32[B,N,3] or None.
         Returns the device tensor [total, chamfer, trans, rot] (no host sync)."""
         self._c("caae_step_begin", _Engine._p(self.state), self.B)
-        self.forward_losses(visible, target, class_id, translation, axisangle, noise)
+        self.forward_losses(visible, target, class_id, translation, axisangle, noise, start_heads_backward=True)
         self.backward(target)
         self.apply_gradients()
         return self.losses

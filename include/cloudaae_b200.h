@@ -145,6 +145,19 @@ int caae_bn_act_bwd_apply(int R, int C, const float* Y, int ld, const float* sca
                           caae_stream_t stream);
 int caae_colsum(int R, int C, const float* X, int ld, float* out, caae_stream_t stream);
 
+/* Fully connected stack (rows = batch): training-mode batch norm of one layer in ONE launch per direction
+ * (utils/tf_util.py:321-365, 473-525: moments over axis 0).  A CTA owns whole columns, so no partial-sum
+ * buffer is needed.  fwd: statistics + EMA update + scale/shift/mean/invstd + out = relu?(BN(Y)) (out may be
+ * NULL).  bwd: dY = BN/ReLU backward of dOut (dY may alias dOut), dgamma, dbeta. */
+int caae_fc_bn_fwd(int R, int C, const float* Y, int ld, const float* gamma, const float* beta, float* ema_mean,
+                   float* ema_var, const float* decay, float* scale, float* shift, float* save_mean,
+                   float* save_invstd, int relu, float* out, int ldo, caae_stream_t stream);
+int caae_fc_bn_bwd(int R, int C, const float* Y, int ld, const float* scale, const float* shift, const float* mean,
+                   const float* invstd, const float* gamma, int relu, const float* dOut, int lddo, float* dY,
+                   int lddy, float* dgamma, float* dbeta, caae_stream_t stream);
+/* out = a + b + c, n elements (sum of the three branches' gradients w.r.t. the embedding) */
+int caae_add3(long n, const float* a, const float* b, const float* c, float* out, caae_stream_t stream);
+
 /* ==== losses, optimiser, step state ============================================================
  * losses/angular_distance_taylor.py (float64), losses/trans_distance.py, losses/chamfer_loss.py,
  * train_cloudAAE_ycbv.py:166-169,196-273 (bn_decay schedule, total loss, tf.train.AdamOptimizer). */
@@ -184,7 +197,10 @@ int caae_synth_points(int b, int nm, int no, const float* models, const int* cla
  * Hidden point removal on flipped f32[b,n,3] (the viewpoint/origin row is implicit) + convexHull()'s
  * selection: visible ids ascending, the highest one dropped, first `take` rows of org gathered into
  * out_pts f32[b,take,3], short sets padded by picks pad_uniform f32[b,take] in [0,1) (NULL: cyclic).
- * num_vis i32[b] = visible count after the drop; flags_out u8[b,n] (optional) = hull-vertex flags. */
+ * num_vis i32[b] = visible count after the drop; flags_out u8[b,n] (optional) = hull-vertex flags.
+ * Visible-prefix mode: when take + 1 < n and flags_out is NULL only the first `take` visible points are
+ * consumed, so the kernel classifies points in growing index windows and stops once take + 1 visible
+ * ones are known; out_pts is unchanged by this, num_vis then is a lower bound (>= take) of the count. */
 int caae_hpr_select(int b, int n, const float* flipped, const float* org, int org_stride_pts, int take,
                     const float* pad_uniform, float* out_pts, int* num_vis, unsigned char* flags_out,
                     caae_stream_t stream);

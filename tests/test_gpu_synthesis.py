@@ -118,6 +118,31 @@ def test_hpr_duplicates_and_padding_draws():
     assert (vis2[0, r].cpu().numpy() == want).all() and (vis2[0, :nv].cpu().numpy() == P[0, ids]).all()
 
 
+@pytest.mark.parametrize("num_point", [256, 64, 16])
+def test_hpr_visible_prefix_mode_equals_full_classification(num_point):
+    """The training path classifies points in growing index windows and stops once num_point + 1 visible
+    ones are known (include/cloudaae_b200.h, caae_hpr_select); its rows must equal the first rows of the
+    full convexHull() output on the same flipped clouds (small num_point forces several windows)."""
+    b = 48
+    syn = SegmentSynthesizer(load_models_xyz(), b, num_point, seed=5)
+    cls, ax, tr = _poses(b, 21)
+    c, a, t = torch.from_numpy(cls).cuda(), torch.from_numpy(ax).cuda(), torch.from_numpy(tr).cuda()
+    visible, target, _ = syn.synthesize(c, a, t)
+    zero = torch.zeros(b, 1, 3, device="cuda")
+    for flipped, org, got, pad_u, num in ((syn.flip_all, syn.points, visible, syn.pad_u, syn.num_vis),
+                                          (syn.flip_org, syn.points[:, :syn.nm].contiguous(), target, syn.pad_u_org,
+                                           syn.num_vis_org)):
+        take = got.shape[1]
+        pad = torch.rand(b, flipped.shape[1] + 1, device="cuda")
+        pad[:, :take] = pad_u
+        full, full_num = HPR.convexHull(torch.cat([flipped, zero], 1), torch.cat([org, zero], 1), pad_uniform=pad)
+        assert torch.equal(full[:, :take], got)
+        num = num.long()
+        exact = num == full_num
+        assert bool((exact | ((num >= take) & (full_num >= num))).all())
+        assert bool(exact[full_num < take].all())     # short visible sets are always counted exactly
+
+
 def test_fused_synthesizer_feeds_training():
     from cloudaae_b200.train import CloudAAETrainer
     b, n = 8, 256
