@@ -314,7 +314,11 @@ def run_ours_train(args, rank, world, local_rank):
     syn = SegmentSynthesizer(load_models_xyz(device=dev), B, TRAIN_N, seed=1234 + rank)
     pool_h = pose_batches(B, seed=rank)
     pool_d = [{k: torch.from_numpy(v).to(dev) for k, v in bt.items()} for bt in pool_h]
-    static = tr.capture_online(syn, *[pool_d[0][k] for k in TRAIN_KEYS])
+    # one CUDA graph per step; by default the synthesis of batch i+1 runs as a parallel branch next to the
+    # train step of batch i (the reference's tf.data prefetch(1), train_cloudAAE_ycbv.py:115)
+    pipelined = os.environ.get("CLOUDAAE_PIPELINE", "1") != "0"
+    capture = tr.capture_online_pipelined if pipelined else tr.capture_online
+    static = capture(syn, *[pool_d[0][k] for k in TRAIN_KEYS])
 
     def load(i, src):  # refresh the graph's static pose records
         for dst, k in zip(static, TRAIN_KEYS):
@@ -415,6 +419,9 @@ def run_ours_train(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32 (dgcnn_agg contractions: tf32 multiply, f32 accumulate)",
         "data": "synthetic: committed YCB model fixture x fixture pose records, Philox occluders/noise, random-init weights",
         "config": train_config(world, {"cuda_graph": True,
+                                       "synthesis": "on-line, inside the timed step" +
+                                       ("; batch i+1 is synthesized next to the train step of batch i (prefetch 1, "
+                                        "as tf.data prefetch(1) in the reference)" if pipelined else ""),
                                        "l2": "per-step working set (~0.5 GB of activations) exceeds the 126 MB L2; no flush"}),
         "roofline": roofline,
         "stage_ms": {"synthesis": t_syn, "train_step_total": ms},

@@ -12,6 +12,11 @@
 // (256*chunk + 8l ..) as two LDS.128 and the 8 query values as two broadcast LDS.128: 64 FFMA per
 // 4 LDS.  Selection is k rounds of "lane-local min, REDUX min over the warp, REDUX min over the
 // matching indices", merged across chunks through a k-entry list per row.
+// Selection (per row, the whole warp): a threshold T with at least k candidates <= T is found from the
+// 32 lane-local minima (REDUX rounds), the few candidates <= T (typically k..k+4) are compacted into one
+// per lane through a 32-slot staging row, ranked by counting (lexicographic (distance, index), so ties
+// go to the lower index) and the ranks < k are written out — ~2.5x fewer instructions than k rounds of
+// arg-min over all 9 slots of every lane, which remains as the fallback when more than 32 survive.
 #include "common.cuh"
 
 namespace caae {
@@ -37,6 +42,8 @@ knn_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __res
   float* sqq = sqc + KNN_CHUNK;                   // [KNN_QROWS]
   uint32_t* lkey = reinterpret_cast<uint32_t*>(sqq + KNN_QROWS);  // [KNN_QROWS][KNN_MAXK]
   int* lidx = reinterpret_cast<int*>(lkey + KNN_QROWS * KNN_MAXK);
+  uint32_t* stage_k = reinterpret_cast<uint32_t*>(lidx + KNN_QROWS * KNN_MAXK);  // [warps][32]
+  int* stage_i = reinterpret_cast<int*>(stage_k + (KNN_THREADS / 32) * 32);
 
   const int cloud = blockIdx.y;
   const int q0 = blockIdx.x * KNN_QROWS;
@@ -81,8 +88,9 @@ knn_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __res
     for (int ch = 0; ch < c; ++ch) {
       const float4 a0 = *reinterpret_cast<const float4*>(QT + ch * KNN_QT_LD + warp * 8);
       const float4 a1 = *reinterpret_cast<const float4*>(QT + ch * KNN_QT_LD + warp * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(XT + ch * KNN_XT_LD + lane * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(XT + ch * KNN_XT_LD + lane * 8 + 4);
+      // lane l owns candidates 4l..4l+3 and 128+4l..128+4l+3 of the chunk: both LDS.128 are conflict-free
+      const float4 b0 = *reinterpret_cast<const float4*>(XT + ch * KNN_XT_LD + lane * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(XT + ch * KNN_XT_LD + KNN_CHUNK / 2 + lane * 4);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -93,9 +101,15 @@ knn_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __res
 
     // ---- selection, one row at a time (the whole warp works on the same row)
     float sj[8];
+    int cj[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sj[j] = sqc[lane * 8 + j];
-    const int jbase = j0 + lane * 8;
+    for (int j = 0; j < 8; ++j) {
+      const int cl = (j < 4) ? lane * 4 + j : KNN_CHUNK / 2 + lane * 4 + (j - 4);   // position in the chunk
+      sj[j] = sqc[cl];
+      cj[j] = j0 + cl;
+    }
+    uint32_t* wk = stage_k + warp * 32;
+    int* wi = stage_i + warp * 32;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = warp * 8 + i;
@@ -105,27 +119,66 @@ knn_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __res
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = __fadd_rn(__fadd_rn(si, __fmul_rn(-2.f, acc[i][j])), sj[j]);
-        const bool ok = (jbase + j) < n;
+        const bool ok = cj[j] < n;
         key[j] = ok ? sortable(d) : 0xffffffffu;
-        cidx[j] = ok ? (jbase + j) : 0x7fffffff;
+        cidx[j] = ok ? cj[j] : 0x7fffffff;
       }
       // 9th slot: the row's running list from earlier chunks (lane l holds entry l)
       key[8] = (lane < k) ? lkey[row * KNN_MAXK + lane] : 0xffffffffu;
       cidx[8] = (lane < k) ? lidx[row * KNN_MAXK + lane] : 0x7fffffff;
       __syncwarp();
-      for (int r = 0; r < k; ++r) {
-        uint32_t lmin = key[0];
+      // threshold: the smallest T such that at least k of the 32 lane-local minima are <= T
+      uint32_t lmin = key[0];
 #pragma unroll
-        for (int j = 1; j < 9; ++j) lmin = min(lmin, key[j]);
-        const uint32_t wmin = __reduce_min_sync(0xffffffffu, lmin);
-        int lcand = 0x7fffffff;
+      for (int j = 1; j < 9; ++j) lmin = min(lmin, key[j]);
+      uint32_t T = 0;
+      for (int got = 0; got < k;) {
+        T = __reduce_min_sync(0xffffffffu, lmin);
+        got += __popc(__ballot_sync(0xffffffffu, lmin == T));
+        if (lmin == T) lmin = 0xffffffffu;
+        if (T == 0xffffffffu) break;   // fewer than k finite candidates in this chunk + list
+      }
+      int cnt = 0;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) lcand = (key[j] == wmin) ? min(lcand, cidx[j]) : lcand;
-        const int widx = __reduce_min_sync(0xffffffffu, lcand);
+      for (int j = 0; j < 9; ++j) cnt += (key[j] <= T && cidx[j] != 0x7fffffff) ? 1 : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total <= 32) {
+        int off = incl - cnt;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-          if (cidx[j] == widx) { key[j] = 0xffffffffu; cidx[j] = 0x7fffffff; }
-        if (lane == r) { lkey[row * KNN_MAXK + r] = wmin; lidx[row * KNN_MAXK + r] = widx; }
+          if (key[j] <= T && cidx[j] != 0x7fffffff) { wk[off] = key[j]; wi[off] = cidx[j]; ++off; }
+        __syncwarp();
+        const uint32_t mk = (lane < total) ? wk[lane] : 0xffffffffu;
+        const int mi = (lane < total) ? wi[lane] : 0x7fffffff;
+        int rank = 0;
+        for (int t = 0; t < total; ++t) {
+          const uint32_t ok = __shfl_sync(0xffffffffu, mk, t);
+          const int oi = __shfl_sync(0xffffffffu, mi, t);
+          rank += (ok < mk || (ok == mk && oi < mi)) ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane < total && rank < k) { lkey[row * KNN_MAXK + rank] = mk; lidx[row * KNN_MAXK + rank] = mi; }
+        // (fewer than k survivors can only happen when chunk + list hold fewer than k points: the tail stays "empty")
+        if (total < k && lane >= total && lane < k) { lkey[row * KNN_MAXK + lane] = 0xffffffffu; lidx[row * KNN_MAXK + lane] = 0x7fffffff; }
+      } else {
+        // fallback (mass ties at the threshold): k rounds of warp-wide arg-min
+        for (int r = 0; r < k; ++r) {
+          uint32_t lm = key[0];
+#pragma unroll
+          for (int j = 1; j < 9; ++j) lm = min(lm, key[j]);
+          const uint32_t wmin = __reduce_min_sync(0xffffffffu, lm);
+          int lcand = 0x7fffffff;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) lcand = (key[j] == wmin) ? min(lcand, cidx[j]) : lcand;
+          const int widx = __reduce_min_sync(0xffffffffu, lcand);
+#pragma unroll
+          for (int j = 0; j < 9; ++j)
+            if (cidx[j] == widx) { key[j] = 0xffffffffu; cidx[j] = 0x7fffffff; }
+          if (lane == r) { lkey[row * KNN_MAXK + r] = wmin; lidx[row * KNN_MAXK + r] = widx; }
+        }
       }
       __syncwarp();
     }
@@ -149,7 +202,7 @@ extern "C" int caae_knn(int b, int n, int c, int k, const float* x, int ldx, int
   CAAE_RETURN_IF(!x || !idx, CAAE_E_NULLPTR);
   CAAE_RETURN_IF(b > 65535, CAAE_E_BADSHAPE);
   const size_t smem = sizeof(float) * ((size_t)c * (KNN_XT_LD + KNN_QT_LD) + KNN_CHUNK + KNN_QROWS) +
-                      sizeof(int) * 2 * KNN_QROWS * KNN_MAXK;
+                      sizeof(int) * 2 * KNN_QROWS * KNN_MAXK + sizeof(int) * 2 * KNN_THREADS;
   CAAE_RETURN_IF(smem > 220 * 1024, CAAE_E_UNSUPPORTED);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -26,8 +26,13 @@
 // fixtures the visible sets are identical (tests/test_gpu_synthesis.py reports the IoU).
 //
 // One CTA (1024 threads) per cloud; everything a cloud needs lives in shared memory.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "hpr_lp.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace caae {
 
@@ -221,6 +226,19 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) {
   return __hiloint2double(hi, lo);
 }
 
+// a / b for b > 0 in the normal range: reciprocal seed + two Newton steps + one residual correction
+// (<= 1 ulp).  The compiler's IEEE division tests every quotient and sends the whole warp through a
+// ~65-instruction slow path whenever one lane's numerator or quotient is zero or tiny — which some lane
+// of almost every clip is (measured: 13 % of the kernel's instructions).
+__device__ __forceinline__ double div_pos(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  r = fma(fma(-b, r, 1.0), r, r);
+  r = fma(fma(-b, r, 1.0), r, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+
 // Persistent LP solver: every 8-lane GROUP of the calling warp runs the incremental LP of one point
 // (the math of hpr::lp_lane, eight constraints per step), and fetches its next point the moment it
 // finishes one, so the four groups of a warp never wait for each other.  One loop body serves the
@@ -296,7 +314,8 @@ __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch
       const int src = gbase + (start_clip ? fv : 0);
       const double bdu = shfl_d(du, src), bdv = shfl_d(dv, src), brhs = shfl_d(rhs, src);
       if (start_clip) {   // the new optimum lies on the violated constraint's boundary line p0 + t (da, db)
-        const double inv = brhs / (bdu * bdu + bdv * bdv);
+        const double br2 = bdu * bdu + bdv * bdv;
+        const double inv = div_pos(brhs, br2 > 0.0 ? br2 : 1.0);
         p0a = bdu * inv; p0b = bdv * inv; da = -bdv; db = bdu;
         ln = -1.0; ld = 0.0; hn = 1.0; hd = 0.0; infeas = false;
         qend = p + fv; p = p + fv + 1; q = 0;
@@ -304,7 +323,9 @@ __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch
       }
     }
     if (__any_sync(kFull, end_clip)) {
-      double lo = ld > 0.0 ? ln / ld : -INFINITY, hi = hd > 0.0 ? hn / hd : INFINITY;
+      // (absent bounds divide by 1)
+      const double lds = ld > 0.0 ? ld : 1.0, hds = hd > 0.0 ? hd : 1.0;
+      double lo = ld > 0.0 ? div_pos(ln, lds) : -INFINITY, hi = hd > 0.0 ? div_pos(hn, hds) : INFINITY;
 #pragma unroll
       for (int m = 1; m < 8; m <<= 1) { lo = fmax(lo, shfl_xor_d(lo, m)); hi = fmin(hi, shfl_xor_d(hi, m)); }
       const unsigned binf = (__ballot_sync(kFull, infeas) >> gbase) & 0xFFu;
@@ -341,8 +362,16 @@ __device__ long long g_hpr_timing[512 * 8];
 
 __global__ void __launch_bounds__(SY_THREADS)
 hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
-  // CTA -> (job, cloud): all clouds of job 0 first (the caller puts the larger clouds there), then job 1
-  const HprJob& J = jobs.job[blockIdx.x / jobs.b];
+  // One thread-block CLUSTER per cloud.  Every CTA of the cluster builds the same cell-sorted copy of the
+  // cloud in its own shared memory (the set-up is ~5 % of the work) and then solves the LPs of the sorted
+  // positions p with p % cluster_size == rank: a cloud's latency drops by the cluster size, which is what
+  // balances 2b clouds of very different cost over 148 SMs.  The CTAs only exchange their visible counts
+  // (per index window) and, at the end, their flags, through distributed shared memory.
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int cluster_id = blockIdx.x / csize;
+  // cluster -> (job, cloud): all clouds of job 0 first, then job 1
+  const HprJob& J = jobs.job[cluster_id / jobs.b];
   const int n = J.n, org_stride_pts = J.org_stride_pts, take = J.take;
   const float* __restrict__ flipped = J.flipped;
   const float* __restrict__ org = J.org;
@@ -375,8 +404,9 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
   __shared__ int s_warp_tot[33];
   __shared__ float s_box[4], s_fzrow[hpr::G], s_fzmax;
   __shared__ int s_count, s_queue, s_nlist, s_nwork;
+  __shared__ int s_xchg[2];   // this CTA's visible count of the current index window (double-buffered)
 
-  const int cloud = blockIdx.x % jobs.b, tid = threadIdx.x, lane = tid & 31;
+  const int cloud = cluster_id % jobs.b, tid = threadIdx.x, lane = tid & 31;
   const float* __restrict__ f = flipped + (size_t)cloud * n * 3;
 
   long long tk[6] = {0, 0, 0, 0, 0, 0};
@@ -407,11 +437,17 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
   cell_fill[tid] = 0;
   __syncthreads();
 
+  // grid cell of a point from its fp32 (u, v): the set-up and every later lookup (F4[p].x/.y hold the
+  // same fp32 values) evaluate the same expression, so no per-position cell table or search is needed
+  const float cell_gx = (float)G / s_box[2], cell_gy = (float)G / s_box[3];
+  auto cell_of = [&](float uf, float vf) {
+    int cx = (int)((uf - s_box[0]) * cell_gx), cy = (int)((vf - s_box[1]) * cell_gy);
+    cx = min(max(cx, 0), G - 1); cy = min(max(cy, 0), G - 1);
+    return cy * G + cx;
+  };
   // ---- cells; unordered fill of the cell lists
   for (int i = tid; i < n; i += SY_THREADS) {
-    int cx = (int)(((float)SA[i] - s_box[0]) / s_box[2] * G), cy = (int)(((float)SB[i] - s_box[1]) / s_box[3] * G);
-    cx = min(max(cx, 0), G - 1); cy = min(max(cy, 0), G - 1);
-    const int c = cy * G + cx;
+    const int c = cell_of((float)SA[i], (float)SB[i]);
     cell_of_orig[i] = (unsigned short)c;
     flag[i] = 0;
     atomicAdd(&cell_fill[c], 1);
@@ -496,7 +532,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
   // occluder blobs at the end of the cloud are never solved for.
   const bool prefix = flags_out == nullptr && take + 1 < n;
   int lo = 0, hi = prefix ? min(n, 3 * take) : n;
-  int slot_base = 0, nsurv = 0;
+  int slot_base = 0, nsurv = 0, window = 0;
   const float kh = 0.5f * (float)rho;
   while (true) {
   // ---- phase 1: incremental LP of every point of the window over its 3x3 cell neighbourhood (own grid
@@ -506,7 +542,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
   __syncthreads();
   for (int p = tid; p < n_unique; p += SY_THREADS) {
     const int i = id[p];
-    if (i >= lo && i < hi) wlist[atomicAdd(&s_nwork, 1)] = (unsigned short)p;
+    if (i >= lo && i < hi && p % csize == crank) wlist[atomicAdd(&s_nwork, 1)] = (unsigned short)p;
   }
   __syncthreads();
   const int nwork1 = s_nwork;
@@ -519,7 +555,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
         sa = 0.0; sb = 0.0; p0 = 0;
         if (t < nwork1) {
           const int pos = wlist[t];
-          const int c = hpr::find_cell(cell_start, pos);
+          const int c = cell_of(F4[pos].x, F4[pos].y);
           int A[3], B[3];
           hpr::nbhd_ranges(cell_start, c % G, c / G, hpr::nbhd_halfwidth(cell_start, c), A, B);
           seq = hpr::RangesPlusList(A, B, nullptr, 0);
@@ -570,10 +606,11 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
         const float4 fi = F4[i];
         const double sa = SA[slot], sb = SB[slot];
         const float saf = (float)sa, sbf = (float)sb;
-        const int c = hpr::find_cell(cell_start, i);
+        const int c = cell_of(F4[i].x, F4[i].y);
         const int ccx = c % G, ccy = c / G, nk = hpr::nbhd_halfwidth(cell_start, c);
         const int nx0 = max(ccx - nk, 0), nx1 = min(ccx + nk, G - 1);
-        const float ctru = fi.x - saf / (2.f * kh), ctrv = fi.y - sbf / (2.f * kh);   // disk centre
+        const float inv2kh = 1.f / (2.f * kh);
+        const float ctru = fi.x - saf * inv2kh, ctrv = fi.y - sbf * inv2kh;   // disk centre
         unsigned key = 0;
         bool hidden = false;
         // rows the disk can touch at all (radius from the cloud-wide maximum of w), then row by row
@@ -630,7 +667,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
       if (ne == kHidden || __float_as_uint(F4[slot].w) == 0u) continue;
       if (ne == SY_EXTRA) {   // constraint list full (never seen on the fixtures): the full LP settles it
         const int i = surv[slot];
-        const int c = hpr::find_cell(cell_start, i);
+        const int c = cell_of(F4[i].x, F4[i].y);
         int A[3], B[3], FA[7], FB[7];
         const int nk = hpr::nbhd_halfwidth(cell_start, c);
         hpr::nbhd_ranges(cell_start, c % G, c / G, nk, A, B);
@@ -657,7 +694,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
           if (t < nwork) {
             const int slot = wlist[t];
             const int i = surv[slot];
-            const int c = hpr::find_cell(cell_start, i);
+            const int c = cell_of(F4[i].x, F4[i].y);
             int A[3], B[3];
             hpr::nbhd_ranges(cell_start, c % G, c / G, hpr::nbhd_halfwidth(cell_start, c), A, B);
             const int ne = state[slot];
@@ -692,16 +729,32 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
     if (state[slot] != kHidden) flag[id[surv[slot]]] = 1;
   __syncthreads();
   if (hi >= n) break;
-  {  // enough visible points known?
+  {  // enough visible points known?  (sum over the cluster's CTAs; every CTA takes the same decision)
     int c = 0;
     for (int i = tid; i < hi; i += SY_THREADS) c += flag[i];
     int vis_known;
     block_excl_scan(c, s_warp_tot, vis_known);
+    if (csize > 1) {
+      if (tid == 0) s_xchg[window & 1] = vis_known;
+      cluster.sync();
+      for (int r = 0; r < csize; ++r)
+        if (r != crank) vis_known += *cluster.map_shared_rank(&s_xchg[window & 1], r);
+    }
     if (vis_known >= take + 1) break;
   }
-  slot_base = nsurv; lo = hi; hi = min(n, hi + 2 * take);
+  slot_base = nsurv; lo = hi; hi = min(n, hi + 2 * take); ++window;
   }
   if (tid == 0) { tk[4] = clock64(); if (tk[3] == 0) tk[3] = tk[4]; }
+  if (csize > 1) {   // rank 0 collects the other CTAs' flags and finishes alone
+    cluster.sync();
+    if (crank == 0)
+      for (int r = 1; r < csize; ++r) {
+        const unsigned char* rf = cluster.map_shared_rank(flag, r);
+        for (int i = tid; i < n; i += SY_THREADS) flag[i] |= rf[i];
+      }
+    cluster.sync();   // remote shared memory stays valid until every reader is done
+    if (crank != 0) return;
+  }
 
   // ---- ordered compaction by ORIGINAL index (visible ids ascending)
   const int per = (n + SY_THREADS - 1) / SY_THREADS;
@@ -733,7 +786,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
   }
   if (tid == 0) {
     tk[5] = clock64();
-    long long* g = g_hpr_timing + (blockIdx.x % 512) * 8;
+    long long* g = g_hpr_timing + (cluster_id % 512) * 8;
     for (int k = 0; k < 5; ++k) g[k] = tk[k + 1] - tk[k];
     g[5] = nsurv; g[6] = dbg_rounds; g[7] = dbg_resolved;
   }
@@ -791,7 +844,27 @@ static int hpr_launch(int b, int njobs, const HprJob* jobs, caae_stream_t stream
     cudaError_t e = cudaFuncSetAttribute(hpr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  hpr_select_kernel<<<b * njobs, SY_THREADS, smem, as_stream(stream)>>>(J);
+  // cluster size = CTAs per cloud (CAAE_HPR_CLUSTER = 1, 2 or 4; read once).  Measured on B200, batch 128:
+  // stand-alone the kernel is fastest with 2 (1.37 ms vs 1.48 ms), but next to the train step of the
+  // previous batch (CloudAAETrainer.capture_online_pipelined) the extra set-up work of the second CTA costs
+  // more than the shorter tail saves (step 3.00 ms vs 2.81 ms), so the default is 1.
+  static int cluster = 0;
+  if (cluster == 0) {
+    const char* e = getenv("CAAE_HPR_CLUSTER");
+    const int v = e ? atoi(e) : 1;
+    cluster = (v == 1 || v == 2 || v == 4) ? v : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(b * njobs * cluster));
+  cfg.blockDim = dim3(SY_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, hpr_select_kernel, J);
+  if (le != cudaSuccess) return (int)le;
   return CAAE_LAUNCH_STATUS();
 }
 

@@ -419,7 +419,12 @@ class _Engine:
             bn = self.bn[self.enc[-1]]
             self._c("caae_bn_act_pool", B, N, 1024, self._p(self.enc_y[-1]), 1024, self._p(bn["scale"]),
                     self._p(bn["shift"]), 1, self._p(self.emb), self._p(self.argmax))
-        outs = []
+        self.forward_fc(train_fc, decay)
+        outs = [self.fc_y[br[-1]] for br in self.branches]
+        return outs[0], outs[1], outs[2], self.emb, before
+
+    def forward_fc(self, train_fc: bool, decay):
+        """embedding -> the three FC branches (decoder, rotation head, translation head)."""
         for bi in (1, 2, 0):   # heads on side streams, the decoder on the caller's
             st = self.s_branch[bi - 1] if (self.concurrent and bi > 0) else None
             if st is not None: self._fork(st)
@@ -429,8 +434,6 @@ class _Engine:
                     inp = self._fc_fwd(s, inp, train_fc, decay)
         for st in self.s_branch:
             self._join(st)
-        outs = [self.fc_y[br[-1]] for br in self.branches]
-        return outs[0], outs[1], outs[2], self.emb, before
 
     # -- backward (training-mode BN only, like the reference's training graph)
     def backward(self, d_recon, d_rot, d_trans, d_emb_extra=None):
@@ -449,6 +452,11 @@ class _Engine:
             self.d_emb.add_(d_emb_extra)
         if self.after_fc_backward is not None:  # every FC / head gradient is final: start its allreduce
             self.after_fc_backward()
+        self.backward_encoder()
+
+    def backward_encoder(self):
+        """d(embedding) in self.d_emb -> gradients of the encoder variables."""
+        B, N, R, k = self.B, self.N, self.R, self.k
         if self.model == "dgcnn":
             scope = "dgcnn_agg"
             # mean-pool + ReLU + BN backward, in place over the pre-activation

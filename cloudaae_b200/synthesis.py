@@ -43,9 +43,12 @@ class SegmentSynthesizer:
         self.z_points = torch.empty(B, 2, self.no // 2, 3, **f32)
         self.pad_u = torch.empty(B, num_point, **f32)
         self.pad_u_org = torch.empty(B, 4 * num_point, **f32)
-        self.visible = torch.empty(B, num_point, 3, **f32)
-        self.target = torch.empty(B, 4 * num_point, 3, **f32)
-        self.noise = torch.empty(B, num_point, 3, **f32)
+        # the three products of a batch live in ONE flat buffer so a consumer can take a snapshot with one copy
+        self.out_flat = torch.empty(B * 6 * num_point * 3, **f32)
+        nv = B * num_point * 3
+        self.visible = self.out_flat[:nv].view(B, num_point, 3)
+        self.target = self.out_flat[nv:5 * nv].view(B, 4 * num_point, 3)
+        self.noise = self.out_flat[5 * nv:].view(B, num_point, 3)
         self.num_vis = torch.empty(B, dtype=torch.int32, device=self.dev)
         self.num_vis_org = torch.empty(B, dtype=torch.int32, device=self.dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.dev)  # bumped once per batch

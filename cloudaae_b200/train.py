@@ -163,6 +163,50 @@ class CloudAAETrainer:
         static = (class_id.clone(), axisangle.clone(), translation.clone())
         return self._capture(lambda c, a, t: self.train_step_online(synthesizer, c, a, t), static, warmup)
 
+    def capture_online_pipelined(self, synthesizer, class_id, axisangle, translation, warmup: int = 2):
+        """Like capture_online, with the data pipeline's prefetch(1) (train_cloudAAE_ycbv.py:115): ONE graph
+        whose two parallel branches are the train step on batch i (synthesized during the previous replay)
+        and the on-line synthesis of batch i+1 from the pose records currently in the static inputs.  The
+        hidden-point-removal kernel (one cloud per CTA, uneven cloud costs) and the many small model
+        kernels fill each other's idle SMs.  The first replay trains on the batch synthesized here from
+        the arguments.  Every replay still performs one full synthesis and one full train step."""
+        B = self.B
+        rec = torch.empty(7 * B, dtype=torch.float32, device=self.dev)   # pose records of the NEXT batch
+        static = (rec[:B].view(torch.int32), rec[B:4 * B].view(B, 3), rec[4 * B:].view(B, 3))
+        for dst, src in zip(static, (class_id, axisangle, translation)):
+            dst.copy_(src)
+        rec_prev = rec.clone()                                         # records the pending batch was made from
+        rec_cur = rec.clone()                                          # ... of the batch being trained on
+        cur = torch.empty_like(synthesizer.out_flat)
+        n3 = B * self.N * 3
+        cur_vis, cur_tgt, cur_noise = cur[:n3].view(B, self.N, 3), cur[n3:5 * n3].view(B, 4 * self.N, 3), \
+            cur[5 * n3:].view(B, self.N, 3)
+        c_cur, a_cur, t_cur = rec_cur[:B].view(torch.int32), rec_cur[B:4 * B].view(B, 3), rec_cur[4 * B:].view(B, 3)
+        side = torch.cuda.Stream(self.dev)
+
+        def prime():
+            synthesizer.synthesize(*static)
+            rec_prev.copy_(rec)
+
+        def fn(c, a, t):
+            main = torch.cuda.current_stream(self.dev)
+            cur.copy_(synthesizer.out_flat)       # hand over the batch synthesized during the previous replay
+            rec_cur.copy_(rec_prev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rec_prev.copy_(rec)
+                synthesizer.synthesize(c, a, t)
+            self.train_step(cur_vis, cur_tgt, c_cur, t_cur, a_cur, cur_noise)
+            main.wait_stream(side)
+
+        prime()
+        out = self._capture(fn, static, warmup)
+        prime()   # warm-up and capture consumed the primed batch's slot; make the first replay well-defined
+        self.prime_pipeline = prime   # re-synthesize the pending batch from the static records (tests, restarts)
+        # the graph holds raw addresses of these buffers: they must outlive it
+        self._pipeline_keep = (rec, rec_prev, rec_cur, cur, side, synthesizer)
+        return out
+
     def replay(self):
         self._graph.replay()
         return self.losses
