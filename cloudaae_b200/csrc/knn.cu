@@ -127,20 +127,21 @@ knn_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __res
       key[8] = (lane < k) ? lkey[row * KNN_MAXK + lane] : 0xffffffffu;
       cidx[8] = (lane < k) ? lidx[row * KNN_MAXK + lane] : 0x7fffffff;
       __syncwarp();
-      // threshold: the smallest T such that at least k of the 32 lane-local minima are <= T
+      // threshold: T >= the k-th smallest of the 32 lane-local minima, so at least k candidates are <= T
+      // (k rounds of "warp minimum, retire the lanes that hold it"; lanes tied at a minimum retire together,
+      // which only makes T a little larger than necessary)
       uint32_t lmin = key[0];
 #pragma unroll
       for (int j = 1; j < 9; ++j) lmin = min(lmin, key[j]);
       uint32_t T = 0;
-      for (int got = 0; got < k;) {
+      for (int r = 0; r < k; ++r) {
         T = __reduce_min_sync(0xffffffffu, lmin);
-        got += __popc(__ballot_sync(0xffffffffu, lmin == T));
-        if (lmin == T) lmin = 0xffffffffu;
-        if (T == 0xffffffffu) break;   // fewer than k finite candidates in this chunk + list
+        lmin = (lmin == T) ? 0xffffffffu : lmin;
       }
-      int cnt = 0;
+      unsigned pm = 0;   // bit j: slot j survives
 #pragma unroll
-      for (int j = 0; j < 9; ++j) cnt += (key[j] <= T && cidx[j] != 0x7fffffff) ? 1 : 0;
+      for (int j = 0; j < 9; ++j) pm |= (key[j] <= T && cidx[j] != 0x7fffffff) ? (1u << j) : 0u;
+      const int cnt = __popc(pm);
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -149,7 +150,7 @@ knn_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __res
         int off = incl - cnt;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-          if (key[j] <= T && cidx[j] != 0x7fffffff) { wk[off] = key[j]; wi[off] = cidx[j]; ++off; }
+          if (pm & (1u << j)) { wk[off] = key[j]; wi[off] = cidx[j]; ++off; }
         __syncwarp();
         const uint32_t mk = (lane < total) ? wk[lane] : 0xffffffffu;
         const int mi = (lane < total) ? wi[lane] : 0x7fffffff;

@@ -520,15 +520,18 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
       float g = 0.f, acc = 0.f;
       if (MODE >= 2) g = dOut[(base + p) * lddo + ch] * invk;
       const int* nb = s_idx + p * k;
+      // sums over the k neighbours of ONE point in fp32 (k terms), across points in fp64: the fp32->fp64
+      // conversions and DADDs per neighbour were the bottleneck of the two reduction passes
+      float fa = 0.f, fb = 0.f;
       for (int j = 0; j < k; ++j) {
         const int q = nb[j];
         const float z = pv + Qs[q * ES_CH + cl];
         if (MODE == 0) {
-          a += (double)z; b += (double)z * (double)z;
+          fa += z; fb = fmaf(z, z, fb);
         } else if (MODE == 1) {
           acc += fmaxf(fmaf(z, sc, sh), 0.f);
         } else if (MODE == 2) {
-          if (fmaf(z, sc, sh) > 0.f) { a += (double)g; b += (double)g * (double)((z - mu) * is); }
+          if (fmaf(z, sc, sh) > 0.f) { fa += 1.f; fb += (z - mu) * is; }
         } else {
           const float dy = (fmaf(z, sc, sh) > 0.f) ? g : 0.f;
           const float dz = gis * (dy - mdy - (z - mu) * is * mdz);
@@ -536,6 +539,8 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
           atomicAdd(dQs + q * ES_CH + cl, dz);
         }
       }
+      if (MODE == 0) { a += (double)fa; b += (double)fb; }
+      if (MODE == 2) { a += (double)(g * fa); b += (double)(g * fb); }
       if (MODE == 1) out[(base + p) * ldo + ch] = acc * invk;
       if (MODE == 3) out[(base + p) * ldo + ch] = acc;  // dP
     }

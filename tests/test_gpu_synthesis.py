@@ -201,4 +201,4 @@ def test_pipelined_graph_equals_sequential_steps():
     assert torch.allclose(want[0], got[0], rtol=1e-5, atol=1e-6), (want[0], got[0])
     for w, g in zip(want, got):
         assert torch.allclose(w, g, rtol=1e-2, atol=1e-5), (w, g)
-    assert (t_seq.v.flat - t_pipe.v.flat).abs().max().item() < 5e-3
+    assert (t_seq.v.flat - t_pipe.v.flat).abs().mean().item() < 1e-4
