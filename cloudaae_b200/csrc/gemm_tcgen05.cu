@@ -30,6 +30,7 @@
 //            the next 32 M/N elements start LBO = 4096 B later.  Four TMA boxes {32 (M/N), 32 (K rows)}
 //            per stage.  A K-step of 8 rows advances the start address by 1024 B.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -88,6 +89,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
+// tcgen05.wait::ld with the loaded registers as read-write operands: ties every later use of r[] to the wait,
+// so the compiler cannot schedule a consumer (or a spill) of the registers between the load and the wait.
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
+}
+
 // shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 |
 //   [61,64) layout type (2 = SWIZZLE_128B, 1 = SWIZZLE_128B with 32-byte atoms)
@@ -112,6 +125,7 @@ struct GemmParams {
 __global__ void __launch_bounds__(TTHREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const GemmParams p) {
+  __shared__ __align__(16) float s_bias[TBN];
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-byte alignment
   const uint32_t smem_a = base, smem_b = base + TSTAGES * TSTAGE_A;
@@ -193,15 +207,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===== epilogue: warps 2..5 -> TMEM lane quadrants 2,3,0,1 =====
     const int quad = warp & 3;
     const int row = m0 + quad * 32 + lane;
+    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
+    // bias row of the tile -> shared memory during the main loop (keeps L2 latency out of the serial epilogue)
+    for (int t = (int)threadIdx.x - 64; t < TBN; t += 128) s_bias[t] = (add_bias && n0 + t < p.N) ? p.bias[n0 + t] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < TBN; c0 += 32) {
       uint32_t r[32];
       if (num_kb > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_wait_ld(r);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
@@ -214,8 +231,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                    __uint_as_float(r[j + 3]));
-            if (add_bias) {
-              const float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + j);
+            {
+              const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
               v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
             }
             if (p.accumulate) {
@@ -225,10 +242,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             *reinterpret_cast<float4*>(crow + j) = v;
           }
         } else {
-          for (int j = 0; j < ncols; ++j) {
-            float v = __uint_as_float(r[j]) + (add_bias ? p.bias[n0 + c0 + j] : 0.f);
-            if (p.atomic) atomicAdd(crow + j, v);
-            else crow[j] = p.accumulate ? crow[j] + v : v;
+          // (compile-time register indices: a run-time index would put r[] in local memory)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+              const float v = __uint_as_float(r[j]) + s_bias[c0 + j];
+              if (p.atomic) atomicAdd(crow + j, v);
+              else crow[j] = p.accumulate ? crow[j] + v : v;
+            }
           }
         }
       }
@@ -240,6 +261,192 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ---- large-tile variant ------------------------------------------------------------------------------
+// CTA tile (MH x 128) x BN with MH = 2 row halves (two M = 128 accumulators) and BN up to 256 columns.
+// The 128 x 128 kernel above moves 32 KB of operands per 2 x 128 x 128 x 32 FLOP; for the dgcnn_agg
+// contractions (K = 320 forward, K = 1024 data gradient) that makes it L2 -> SM bandwidth bound (measured
+// 6.4 TB/s of operand reads at 209 TFLOP/s).  Larger tiles cut the operand bytes per FLOP: 256 x 160 for the
+// N = 320 data gradient (dY is read twice instead of three times).  K-major or MN-major A; B either major.
+// One CTA per SM (3-4 stages of 52-64 KB), 512 TMEM columns: accumulator of row block h at column ACC_COLS h.
+// Third shape: the weight gradient [320,1024] = X^T dY (both operands MN-major, K = B*N rows, split-K): MH = 3
+// row blocks cover all 320 rows (the last block is half padding, zero-filled by TMA), so dY — the large
+// operand — is read once instead of three times; partial tiles are combined with 16-byte vector reductions.
+template <int BN, int MH_>
+struct BigCfg {
+  static constexpr int MH = MH_;
+  static constexpr int ACC_COLS = (BN <= 128) ? 128 : 256;         // TMEM column pitch of the row blocks
+  static constexpr uint32_t STAGE_A = MH * TBM * TBK * 4;          // 16 KB per row block
+  static constexpr uint32_t STAGE_B = BN * TBK * 4;                // 32 KB (BN = 256) / 20 KB (160) / 16 KB (128)
+  static constexpr int STAGES = (STAGE_A + STAGE_B > 56 * 1024) ? 3 : 4;
+  static constexpr uint32_t SMEM = STAGES * (STAGE_A + STAGE_B) + 1024 + 256;
+  static_assert(MH * ACC_COLS <= 512, "TMEM has 512 columns");
+};
+
+constexpr int BIG_THREADS = 320;   // TMA warp, MMA warp, eight epilogue warps
+
+template <int BN, int MH_, bool A_MN>
+__global__ void __launch_bounds__(BIG_THREADS)
+gemm_tf32_big_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const GemmParams p) {
+  using Cfg = BigCfg<BN, MH_>;
+  constexpr int ST = Cfg::STAGES, MH = Cfg::MH;
+  __shared__ __align__(16) float s_bias[BN];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base, smem_b = base + ST * Cfg::STAGE_A;
+  const uint32_t bars = smem_b + ST * Cfg::STAGE_B;
+  const uint32_t full0 = bars, empty0 = bars + 8 * ST, tmem_full = bars + 16 * ST, tmem_slot = tmem_full + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * (MH * TBM), n0 = blockIdx.x * BN;
+  const int num_kb_total = (p.K + TBK - 1) / TBK;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int num_kb = min(num_kb_total, kb0 + p.kb_per_split) - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % ST;
+        const uint32_t ph = (i / ST) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_A + Cfg::STAGE_B);
+        const int k0 = (kb0 + i) * TBK;
+        const uint32_t da = smem_a + s * Cfg::STAGE_A, db = smem_b + s * Cfg::STAGE_B;
+        if (A_MN) {
+#pragma unroll
+          for (int c = 0; c < MH * TBM / 32; ++c) tma_load_2d(da + c * 4096, &map_a, full0 + 8 * s, m0 + 32 * c, k0);
+        } else {
+#pragma unroll
+          for (int h = 0; h < MH; ++h) tma_load_2d(da + h * TSTAGE_A, &map_a, full0 + 8 * s, k0, m0 + h * TBM);
+        }
+        if (p.b_mn) {
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) tma_load_2d(db + c * 4096, &map_b, full0 + 8 * s, n0 + 32 * c, k0);
+        } else {
+          tma_load_2d(db, &map_b, full0 + 8 * s, k0, n0);   // box {32, BN}
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t b_lbo = p.b_mn ? 4096u : 16u, b_kstep = p.b_mn ? 1024u : 32u;
+      const uint32_t b_sbo = p.b_mn ? 512u : 1024u, b_lt = p.b_mn ? 1u : 2u;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % ST;
+        const uint32_t ph = (i / ST) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t da = smem_a + s * Cfg::STAGE_A, db = smem_b + s * Cfg::STAGE_B;
+#pragma unroll
+        for (int k = 0; k < TBK / 8; ++k) {
+          const uint64_t bdesc = make_smem_desc(db + k * b_kstep, b_lbo, b_sbo, b_lt);
+#pragma unroll
+          for (int h = 0; h < MH; ++h) {
+            const uint64_t adesc = A_MN ? make_smem_desc(da + h * TSTAGE_A + k * 1024u, 4096u, 512u, 1u)
+                                        : make_smem_desc(da + h * TSTAGE_A + k * 32u, 16u, 1024u, 2u);
+            umma_tf32(tmem_base + (uint32_t)(h * Cfg::ACC_COLS), adesc, bdesc, p.idesc, (uint32_t)((i | k) != 0));
+          }
+        }
+        umma_commit(empty0 + 8 * s);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: EIGHT warps (2..9).  A warp may only read the TMEM lane quadrant warp % 4, so two warps
+    // share each quadrant and split the 32-column chunks between them (even / odd).  With one CTA per SM the
+    // epilogue is serial after the main loop: twice the warps and a TMEM load issued one chunk ahead of the
+    // stores roughly halve it.
+    const int quad = warp & 3, part = (warp - 2) >> 2;
+    // the tile's bias row goes to shared memory while the main loop runs: a global load per output chunk
+    // here would expose the (loaded) L2 latency once per chunk — measured +55 us on the dgcnn_agg forward GEMM
+    const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
+    for (int t = (int)threadIdx.x - 64; t < BN; t += 256) s_bias[t] = (add_bias && n0 + t < p.N) ? p.bias[n0 + t] : 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    constexpr int NC = BN / 32;                       // chunks per row block
+    constexpr int NWORK = MH * NC;                    // (row block, chunk) items; this warp takes item % 2 == part
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    auto taddr = [&](int w) { return tlane + (uint32_t)((w / NC) * Cfg::ACC_COLS + (w % NC) * 32); };
+    auto store_item = [&](uint32_t (&r)[32], int w) {
+      if (num_kb <= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      const int h = w / NC, c0 = (w % NC) * 32;
+      const int row = m0 + h * TBM + quad * 32 + lane;
+      if (row >= p.M || n0 + c0 >= p.N) return;
+      float* crow = p.C + (size_t)row * p.ldc + n0 + c0;
+      const int ncols = min(32, p.N - (n0 + c0));
+      if (ncols == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (p.atomic) {   // split-K partial tile: red.global.add.v4.f32
+            atomicAdd(reinterpret_cast<float4*>(crow + j), v);
+            continue;
+          }
+          if (p.accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(crow + j);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *reinterpret_cast<float4*>(crow + j) = v;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {   // compile-time register indices (a run-time index would put r[] in local memory)
+          if (j < ncols) {
+            const float v = __uint_as_float(r[j]) + s_bias[c0 + j];
+            if (p.atomic) atomicAdd(crow + j, v);
+            else crow[j] = p.accumulate ? crow[j] + v : v;
+          }
+        }
+      }
+    };
+    // two register buffers: the TMEM load of the next item is in flight while the current one is stored
+    uint32_t r0[32], r1[32];
+    const bool have = num_kb > 0;
+    if (part < NWORK && have) tmem_ld32(taddr(part), r0);
+#pragma unroll 1
+    for (int w = part; w < NWORK; w += 4) {
+      tmem_wait_ld(r0);
+      if (w + 2 < NWORK && have) tmem_ld32(taddr(w + 2), r1);
+      store_item(r0, w);
+      if (w + 2 < NWORK) {
+        tmem_wait_ld(r1);
+        if (w + 4 < NWORK && have) tmem_ld32(taddr(w + 4), r0);
+        store_item(r1, w + 2);
+      }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
@@ -327,6 +534,54 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
             ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
   const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
   const int num_kb = (K + TBK - 1) / TBK;
+  // the three big dgcnn_agg-shaped contractions: large tiles, one CTA per SM (see gemm_tf32_big_kernel)
+  static const bool big_enabled = [] { const char* e = getenv("CAAE_GEMM_BIG"); return !(e && e[0] == '0'); }();
+  // (N % 256 == 0 shapes such as the dgcnn_agg forward GEMM stay on the 128 x 128 kernel: measured 85 us vs
+  // 94 us for a 256 x 256 tile, whose serial epilogue of 256 KB per tile outweighs the saved operand traffic)
+  const bool big_fwd = !transa && M >= 256 * kNumSMs / 2 && K >= 256 && N >= 160 && N % 160 == 0 && N % 256 != 0;
+  const bool big_wgrad = transa && !transb && M > 256 && M <= 384 && N % 128 == 0 && N >= 512 && K >= 64 * TBK * 8;
+  if (big_enabled && (big_fwd || big_wgrad)) {
+    const int bn = big_wgrad ? 128 : 160;
+    const int mh = big_wgrad ? 3 : 2;
+    CUtensorMap map_a2, map_b2;
+    rc = transa ? make_map(&map_a2, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK, true)
+                : make_map(&map_a2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
+    if (rc) return rc;
+    rc = transb ? make_map(&map_b2, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, (uint32_t)bn, false)
+                : make_map(&map_b2, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
+    if (rc) return rc;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+              ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    const int tiles_big = (N / bn) * ((M + mh * TBM - 1) / (mh * TBM));
+    int sp = 1;
+    if (big_wgrad) {   // split K so that the grid fills the SMs once
+      sp = kNumSMs / tiles_big;
+      if (sp < 1) sp = 1;
+      if (sp > num_kb / 8) sp = num_kb / 8;
+    }
+    p.kb_per_split = (num_kb + sp - 1) / sp;
+    sp = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.atomic = sp > 1;
+    p.accumulate = p.atomic ? 0 : accumulate;
+    if (p.atomic && !accumulate) {
+      const long total = (long)M * N;
+      const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+      zero_matrix2_kernel<<<blocks, 256, 0, s>>>(M, N, C, ldc);
+    }
+    dim3 grid(N / bn, (M + mh * TBM - 1) / (mh * TBM), sp);
+    CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
+#define CAAE_LAUNCH_BIG(BN_, MH_, AMN_)                                                                              \
+    do {                                                                                                             \
+      cudaError_t e_ = cudaFuncSetAttribute(gemm_tf32_big_kernel<BN_, MH_, AMN_>,                                    \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BigCfg<BN_, MH_>::SMEM); \
+      if (e_ != cudaSuccess) return (int)e_;                                                                         \
+      gemm_tf32_big_kernel<BN_, MH_, AMN_><<<grid, BIG_THREADS, BigCfg<BN_, MH_>::SMEM, s>>>(map_a2, map_b2, p);        \
+    } while (0)
+    if (big_wgrad) CAAE_LAUNCH_BIG(128, 3, true);
+    else CAAE_LAUNCH_BIG(160, 2, false);
+#undef CAAE_LAUNCH_BIG
+    return CAAE_LAUNCH_STATUS();
+  }
   int splits = 1;
   const int tiles = tiles_m * tiles_n;
   if (tiles < kNumSMs && num_kb >= 8) {

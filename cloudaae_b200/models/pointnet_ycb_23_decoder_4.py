@@ -210,9 +210,10 @@ class _Engine:
         # the EdgeConv projection next to the kNN search of the same layer.  Every launch of those chains
         # is far too small to fill 148 SMs on its own.  CLOUDAAE_STREAMS=0 serialises everything.
         self.concurrent = os.environ.get("CLOUDAAE_STREAMS", "1") != "0" and self.dev.type == "cuda"
-        self.s_branch = [torch.cuda.Stream(self.dev) for _ in range(2)] if self.concurrent else []
-        self.s_wgrad = [torch.cuda.Stream(self.dev) for _ in range(3)] if self.concurrent else []
-        self.s_enc = torch.cuda.Stream(self.dev) if self.concurrent else None
+        hi = dict(device=self.dev, priority=-1)   # the model's streams outrank the synthesis branch of a pipelined graph
+        self.s_branch = [torch.cuda.Stream(**hi) for _ in range(2)] if self.concurrent else []
+        self.s_wgrad = [torch.cuda.Stream(**hi) for _ in range(3)] if self.concurrent else []
+        self.s_enc = torch.cuda.Stream(**hi) if self.concurrent else None
         self.d_emb_br = torch.empty(3, B, 1024, **f32)
         self._heads_pending = False
 

@@ -13,6 +13,8 @@ fp32 gradient buffer per step followed by a 1/world scale inside the Adam kernel
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _capi
@@ -142,7 +144,10 @@ class CloudAAETrainer:
         torch.cuda.current_stream(self.dev).wait_stream(s)
         self._graph = torch.cuda.CUDAGraph()
         before = _capi.COUNTER[0]
-        with torch.cuda.graph(self._graph):
+        # capture on a HIGH-priority stream: kernel nodes inherit it, so the train step's kernels are
+        # dispatched ahead of the low-priority synthesis branch of the pipelined graph
+        self._capture_stream = torch.cuda.Stream(self.dev, priority=-1)
+        with torch.cuda.graph(self._graph, stream=self._capture_stream):
             fn(*static)
         self.launches_per_step = _capi.COUNTER[0] - before  # C-ABI launches captured into one step
         # warm-up and capture must not count as training steps
@@ -182,7 +187,7 @@ class CloudAAETrainer:
         cur_vis, cur_tgt, cur_noise = cur[:n3].view(B, self.N, 3), cur[n3:5 * n3].view(B, 4 * self.N, 3), \
             cur[5 * n3:].view(B, self.N, 3)
         c_cur, a_cur, t_cur = rec_cur[:B].view(torch.int32), rec_cur[B:4 * B].view(B, 3), rec_cur[4 * B:].view(B, 3)
-        side = torch.cuda.Stream(self.dev)
+        side = torch.cuda.Stream(self.dev, priority=0 if os.environ.get("CLOUDAAE_SYNTH_PRIORITY", "low") == "low" else -1)
 
         def prime():
             synthesizer.synthesize(*static)

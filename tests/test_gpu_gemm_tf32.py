@@ -21,7 +21,11 @@ def _pad4(x):
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 96), (300, 130, 77), (4096, 1024, 320), (128, 3072, 1024),
-                                   (320, 1024, 8192), (64, 64, 4096), (1, 8, 8)])
+                                   (320, 1024, 8192), (64, 64, 4096), (1, 8, 8),
+                                   (8292, 1024, 320), (20000, 256, 64), (19000, 130, 77),
+                                   # the large-tile kernel: 256 x 256 (forward-like), 256 x 160 (N = 320 data gradient),
+                                   # 3 x 128 rows x 128 with split-K (weight gradient, ta = 1 / tb = 0)
+                                   (19201, 512, 320), (19300, 320, 520), (320, 1024, 16500), (300, 512, 20000)])
 def test_gemm_tf32_layouts(ta, tb, M, N, K):
     g = torch.Generator("cuda").manual_seed(M + 3 * N + 7 * K + ta + 2 * tb)
     a_shape = (K, _pad4(M)) if ta else (M, _pad4(K))
@@ -65,3 +69,24 @@ def test_gemm_tf32_reads_column_slices_in_place():
     _run(0, 0, 2048, 256, 64, X, 320, W, 256, C, 256)
     want = X.double() @ W.double()
     assert (C.double() - want).abs().max() <= 2e-3 * (X.abs().double() @ W.abs().double()).max() / 8
+
+
+def test_gemm_tf32_persistent_agg_shape_aligned_output():
+    """dgcnn_agg forward shape (M = B*N rows, K = 320, N = 1024) with the model's aligned row pitch: the
+    large-tile kernel's float4 epilogue and bias over the full 128 x 4 tile grid."""
+    g = torch.Generator("cuda").manual_seed(11)
+    M, N, K = 32768, 1024, 320
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(K, N, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    C = torch.empty(M, N, device="cuda")
+    _run(0, 0, M, N, K, A, K, B, N, C, N, bias)
+    torch.cuda.synchronize()
+    rows = torch.randint(0, M, (512,), device="cuda", generator=g)
+    rows[:4] = torch.tensor([0, 127, 128, M - 1], device="cuda")
+    want = A[rows].double() @ B.double() + bias.double()
+    scale = (A[rows].abs().double() @ B.abs().double()).max()
+    assert (C[rows].double() - want).abs().max() <= 4e-3 * scale / K ** 0.5
+    # every tile was written (no stale rows): compare column sums against an fp32 matmul
+    ref = A @ B + bias
+    assert (C - ref).abs().max() <= 4e-3 * scale
