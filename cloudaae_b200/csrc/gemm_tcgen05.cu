@@ -226,7 +226,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (row < p.M) {
         float* crow = p.C + (size_t)row * p.ldc + n0 + c0;
         const int ncols = min(32, p.N - (n0 + c0));
-        if (ncols == 32 && !p.atomic && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -234,6 +234,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             {
               const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
               v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            }
+            if (p.atomic) {   // split-K partial tile: one red.global.add.v4.f32 per four outputs
+              atomicAdd(reinterpret_cast<float4*>(crow + j), v);
+              continue;
             }
             if (p.accumulate) {
               const float4 o = *reinterpret_cast<const float4*>(crow + j);
@@ -450,6 +454,166 @@ gemm_tf32_big_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
 }
 
+// ---- persistent variant for tall, short-K, wide-N problems (dgcnn_agg / pn_conv5 forward) -------------------
+// 256 x 128 tiles (two row blocks share one B stage: 48 KB of operands per 2 x 128 x 128 x 32 MACs, 1.5x
+// fewer operand bytes per FLOP than the 128 x 128 kernel), one CTA per SM walking over tiles, and TWO
+// accumulator sets in TMEM (2 x 256 columns): the eight epilogue warps drain tile i (128 KB of stores)
+// while the TMA and MMA warps run the main loop of tile i+1, so the output stream — the real bound of a
+// K = 320 GEMM with a 134 MB result — overlaps the tensor work instead of following it.  Barrier set-up,
+// TMEM allocation and descriptor fetch happen once per CTA.  K-major A; B either major; no split-K.
+constexpr int PS_STAGES = 4;
+constexpr uint32_t PS_STAGE_A = 2 * TSTAGE_A, PS_STAGE_B = TSTAGE_B;
+constexpr uint32_t PS_SMEM = PS_STAGES * (PS_STAGE_A + PS_STAGE_B) + 1024 + 256;
+constexpr int PS_MAXN = 2048;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(BIG_THREADS)
+gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const GemmParams p, const int tiles_m, const int tiles_n) {
+  __shared__ __align__(16) float s_bias[PS_MAXN];
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base, smem_b = base + PS_STAGES * PS_STAGE_A;
+  const uint32_t bars = smem_b + PS_STAGES * PS_STAGE_B;
+  const uint32_t full0 = bars, empty0 = bars + 8 * PS_STAGES;
+  const uint32_t tfull0 = empty0 + 8 * PS_STAGES, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (p.K + TBK - 1) / TBK;
+  const int tiles = tiles_m * tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PS_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int t = threadIdx.x; t < p.N; t += BIG_THREADS) s_bias[t] = (p.bias != nullptr) ? p.bias[t] : 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer: tiles id = blockIdx.x, + gridDim.x, ...; id -> (row tile id / tiles_n, column tile id % tiles_n),
+    // so the CTAs of one wave share A row tiles in L2 =====
+    if (lane == 0) {
+      int it = 0;
+      for (int id = blockIdx.x; id < tiles; id += gridDim.x) {
+        const int m0 = (id / tiles_n) * (2 * TBM), n0 = (id % tiles_n) * TBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % PS_STAGES;
+          const uint32_t ph = (it / PS_STAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, PS_STAGE_A + PS_STAGE_B);
+          const int k0 = kb * TBK;
+          const uint32_t da = smem_a + s * PS_STAGE_A, db = smem_b + s * PS_STAGE_B;
+          tma_load_2d(da, &map_a, full0 + 8 * s, k0, m0);
+          tma_load_2d(da + TSTAGE_A, &map_a, full0 + 8 * s, k0, m0 + TBM);
+          if (p.b_mn) {
+#pragma unroll
+            for (int c = 0; c < TBN / 32; ++c) tma_load_2d(db + c * 4096, &map_b, full0 + 8 * s, n0 + 32 * c, k0);
+          } else {
+            tma_load_2d(db, &map_b, full0 + 8 * s, k0, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t b_lbo = p.b_mn ? 4096u : 16u, b_kstep = p.b_mn ? 1024u : 32u;
+      const uint32_t b_sbo = p.b_mn ? 512u : 1024u, b_lt = p.b_mn ? 1u : 2u;
+      int it = 0, lt = 0;
+      for (int id = blockIdx.x; id < tiles; id += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(tempty0 + 8 * acc, (uint32_t)(((lt >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator set
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % PS_STAGES;
+          const uint32_t ph = (it / PS_STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t da = smem_a + s * PS_STAGE_A, db = smem_b + s * PS_STAGE_B;
+#pragma unroll
+          for (int k = 0; k < TBK / 8; ++k) {
+            const uint64_t bdesc = make_smem_desc(db + k * b_kstep, b_lbo, b_sbo, b_lt);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint64_t adesc = make_smem_desc(da + h * TSTAGE_A + k * 32u, 16u, 1024u, 2u);
+              umma_tf32(tacc + (uint32_t)(h * TBN), adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
+            }
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    // ===== epilogue: eight warps; two per TMEM lane quadrant, splitting the (row block, 32-column chunk) items =====
+    const int quad = warp & 3, part = (warp - 2) >> 2;
+    constexpr int NC = TBN / 32, NWORK = 2 * NC;
+    int lt = 0;
+    for (int id = blockIdx.x; id < tiles; id += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      const int m0 = (id / tiles_n) * (2 * TBM), n0 = (id % tiles_n) * TBN;
+      mbar_wait(tfull0 + 8 * acc, (uint32_t)((lt >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
+      auto taddr = [&](int w) { return tlane + (uint32_t)((w / NC) * TBN + (w % NC) * 32); };
+      auto store_item = [&](uint32_t (&r)[32], int w) {
+        const int h = w / NC, c0 = (w % NC) * 32;
+        const int row = m0 + h * TBM + quad * 32 + lane;
+        if (row >= p.M) return;
+        float* crow = p.C + (size_t)row * p.ldc + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          const float4 bv = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + j);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (p.accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(crow + j);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *reinterpret_cast<float4*>(crow + j) = v;
+        }
+      };
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr(part), r0);
+#pragma unroll 1
+      for (int w = part; w < NWORK; w += 4) {
+        tmem_wait_ld(r0);
+        if (w + 2 < NWORK) tmem_ld32(taddr(w + 2), r1);
+        store_item(r0, w);
+        if (w + 2 < NWORK) {
+          tmem_wait_ld(r1);
+          if (w + 4 < NWORK) tmem_ld32(taddr(w + 4), r0);
+          store_item(r1, w + 2);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 __global__ void zero_matrix2_kernel(int M, int N, float* __restrict__ C, int ldc) {
   const long total = (long)M * N;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
@@ -534,6 +698,29 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
             ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
   const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
   const int num_kb = (K + TBK - 1) / TBK;
+  // tall / wide / short-K forward contractions: persistent 256 x 128 tiles with the epilogue overlapped
+  static const bool persist_enabled = [] { const char* e = getenv("CAAE_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
+  if (persist_enabled && !transa && N % TBN == 0 && N <= PS_MAXN && N >= 512 && M >= 256 * kNumSMs / 2 && num_kb >= 2 &&
+      num_kb <= 16 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 3) == 0)) {
+    CUtensorMap map_a2, map_b2;
+    rc = make_map(&map_a2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
+    if (rc) return rc;
+    rc = transb ? make_map(&map_b2, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, TBN, false)
+                : make_map(&map_b2, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
+    if (rc) return rc;
+    static bool psattr = false;
+    if (!psattr) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM);
+      if (e != cudaSuccess) return (int)e;
+      psattr = true;
+    }
+    const int tm = (M + 2 * TBM - 1) / (2 * TBM), tn = N / TBN;
+    p.kb_per_split = num_kb; p.atomic = 0; p.accumulate = accumulate;
+    const int ctas = tm * tn < kNumSMs ? tm * tn : kNumSMs;
+    gemm_tf32_persist_kernel<<<ctas, BIG_THREADS, PS_SMEM, s>>>(map_a2, map_b2, p, tm, tn);
+    return CAAE_LAUNCH_STATUS();
+  }
   // the three big dgcnn_agg-shaped contractions: large tiles, one CTA per SM (see gemm_tf32_big_kernel)
   static const bool big_enabled = [] { const char* e = getenv("CAAE_GEMM_BIG"); return !(e && e[0] == '0'); }();
   // (N % 256 == 0 shapes such as the dgcnn_agg forward GEMM stay on the 128 x 128 kernel: measured 85 us vs
@@ -586,7 +773,10 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
   const int tiles = tiles_m * tiles_n;
   if (tiles < kNumSMs && num_kb >= 8) {
     splits = (2 * kNumSMs + tiles - 1) / tiles;
-    if (splits > num_kb / 4) splits = num_kb / 4;
+    // >= 16 K blocks per split when K is long: with 147 splits of 7 blocks the [64,256] EdgeConv weight gradient
+    // spent its time in prologues and in 147-way contended reductions (57 us for 1 GFLOP)
+    const int min_kb = num_kb >= 64 ? 16 : 4;
+    if (splits > num_kb / min_kb) splits = num_kb / min_kb;
     if (splits < 1) splits = 1;
   }
   p.kb_per_split = (num_kb + splits - 1) / splits;

@@ -314,8 +314,10 @@ class _Engine:
         weight-bandwidth bound, and its batch-norm backward over only `batch` rows amplifies TF32
         rounding of the pre-activations far beyond the 1e-3 parity budget."""
         fn = "caae_gemm_f32"
-        # (N < 128 would leave half of the kernel's 128 x 128 tile idle: measured slower than the FFMA kernel)
-        if (self.precision == "tf32" and M * N * K >= (1 << 29) and N >= 128 and
+        # large contractions only (>= 2^28 MACs with >= 64 output columns): besides dgcnn_agg these are the
+        # EdgeConv projections and their data / weight gradients (M or K = B*N rows)
+        # (never the FC stack: none of its dimensions is the B*N row count)
+        if (self.precision == "tf32" and M * N * K >= (1 << 28) and N >= 64 and max(M, K) >= 8192 and
                 self.lib.caae_gemm_tf32_supported(ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb)):
             fn = "caae_gemm_tf32"
         self._c(fn, ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), acc)

@@ -71,22 +71,26 @@ def test_gemm_tf32_reads_column_slices_in_place():
     assert (C.double() - want).abs().max() <= 2e-3 * (X.abs().double() @ W.abs().double()).max() / 8
 
 
-def test_gemm_tf32_persistent_agg_shape_aligned_output():
-    """dgcnn_agg forward shape (M = B*N rows, K = 320, N = 1024) with the model's aligned row pitch: the
-    large-tile kernel's float4 epilogue and bias over the full 128 x 4 tile grid."""
-    g = torch.Generator("cuda").manual_seed(11)
-    M, N, K = 32768, 1024, 320
+@pytest.mark.parametrize("M,N,K,tb", [(32768, 1024, 320, 0), (19201, 512, 96, 0), (19000, 1024, 128, 1)])
+def test_gemm_tf32_persistent_forward_shapes(M, N, K, tb):
+    """Tall / wide / short-K forward shapes with the model's aligned row pitch (dgcnn_agg: M = B*N rows,
+    K = 320, N = 1024; pn_conv5: K = 128) take the persistent 256 x 128 kernel: tile walk over both TMEM
+    accumulator sets, ragged last row tile, bias from shared memory, accumulate on top."""
+    g = torch.Generator("cuda").manual_seed(11 + K)
     A = torch.randn(M, K, device="cuda", generator=g)
-    B = torch.randn(K, N, device="cuda", generator=g) * 0.05
+    B = (torch.randn(N, K, device="cuda", generator=g) if tb else torch.randn(K, N, device="cuda", generator=g)) * 0.05
     bias = torch.randn(N, device="cuda", generator=g)
-    C = torch.empty(M, N, device="cuda")
-    _run(0, 0, M, N, K, A, K, B, N, C, N, bias)
+    C = torch.full((M, N), 7.0, device="cuda")
+    _run(0, tb, M, N, K, A, K, B, B.shape[1], C, N, bias)
     torch.cuda.synchronize()
-    rows = torch.randint(0, M, (512,), device="cuda", generator=g)
-    rows[:4] = torch.tensor([0, 127, 128, M - 1], device="cuda")
-    want = A[rows].double() @ B.double() + bias.double()
-    scale = (A[rows].abs().double() @ B.abs().double()).max()
-    assert (C[rows].double() - want).abs().max() <= 4e-3 * scale / K ** 0.5
-    # every tile was written (no stale rows): compare column sums against an fp32 matmul
-    ref = A @ B + bias
-    assert (C - ref).abs().max() <= 4e-3 * scale
+    Bm = B.T if tb else B
+    ref = A @ Bm + bias                                   # fp32 reference for the full-matrix check
+    scale = (A[:256].abs().double() @ Bm.abs().double()).max().item()
+    assert (C - ref).abs().max().item() <= 4e-3 * scale   # every tile written, none stale
+    rows = torch.randint(0, M, (256,), device="cuda", generator=g)
+    rows[:4] = torch.tensor([0, 255, 256, M - 1], device="cuda")
+    want = A[rows].double() @ Bm.double() + bias.double()
+    assert (C[rows].double() - want).abs().max().item() <= 4e-3 * scale / K ** 0.5
+    _run(0, tb, M, N, K, A, K, B, B.shape[1], C, N, None, 1)   # C += A B
+    torch.cuda.synchronize()
+    assert (C[rows].double() - (2 * want - bias.double())).abs().max().item() <= 8e-3 * scale / K ** 0.5
