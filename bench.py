@@ -26,6 +26,20 @@ import numpy as np  # noqa: E402
 
 
 # ----------------------------------------------------------------------------------------------
+def ncu_traffic(kernel_prefix: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed ncu --set full
+    capture (profiles/r1_ncu_traffic.json, written by tools/ncu_traffic.py); (None, reason) when absent."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        data = json.load(open(path))
+    except (OSError, ValueError):
+        return None, "profiles/r1_ncu_traffic.json missing"
+    for name, k in data.get("kernels", {}).items():
+        if name.startswith(kernel_prefix):
+            return k["dram_bytes"], f"profiles/r1_ncu_traffic.json ({data.get('source')}): {name}"
+    return None, f"{kernel_prefix} not in profiles/r1_ncu_traffic.json"
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -405,13 +419,34 @@ def run_ours_train(args, rank, world, local_rank):
     flops = 2.0 * R * 320 * 1024
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0  # TF32 dense = half the measured bf16 rate
     gemms = {"dgcnn_agg_fwd": t_fwd, "dgcnn_agg_dgrad": t_dgrad, "dgcnn_agg_wgrad": t_wgrad}
-    dom = max(gemms, key=gemms.get)
+    gemm_kernel = {"dgcnn_agg_fwd": "gemm_tf32_persist_kernel", "dgcnn_agg_dgrad": "gemm_tf32_big_kernel<160, 2, 0>",
+                   "dgcnn_agg_wgrad": "gemm_tf32_big_kernel<128, 3, 1>"}
+    dom = max(gemms, key=gemms.get)   # the slowest of the three 21.5-GFLOP contractions
     achieved = flops / (gemms[dom] * 1e-3) / 1e12
-    roofline = {"kernel": f"gemm_tf32_kernel ({dom}: 32768 x 1024 x 320, tcgen05 TF32)", "bound": "tensor",
+    traffic, traffic_src = ncu_traffic(gemm_kernel[dom])
+    roofline = {"kernel": f"{gemm_kernel[dom]} ({dom}: 32768 x 1024 x 320, tcgen05 TF32)", "bound": "tensor",
                 "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained / 2)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peaks["source"] + " (bf16 sustained / 2)",
                 "algorithmic_flops_per_launch": flops, "ms_per_launch": gemms[dom],
-                "all_agg_gemms_ms": gemms}
+                "all_agg_gemms_ms": gemms,
+                "all_agg_gemms_tflops": {k: flops / (v * 1e-3) / 1e12 for k, v in gemms.items()}}
+    # the largest single kernel of the step has no closed-form roofline (report it separately)
+    n_all = syn.nm + syn.no
+    pp = _capi.ptr
+
+    def hpr_only():
+        _capi.check(lib.caae_hpr_select_pair(B, n_all, pp(syn.flip_all), syn.N, pp(syn.pad_u), pp(syn.visible),
+                                             pp(syn.num_vis), syn.nm, pp(syn.flip_org), 4 * syn.N, pp(syn.pad_u_org),
+                                             pp(syn.target), pp(syn.num_vis_org), pp(syn.points), n_all, st), "hpr")
+
+    t_hpr = timeit(hpr_only)
+    hpr_bytes = B * 12.0 * (n_all + syn.nm + TRAIN_N + 4 * TRAIN_N)   # flipped clouds in, selected points out
+    synthesis_kernel = {"kernel": "hpr_select_kernel (hidden point removal, both problems of the batch)",
+                        "ms_per_launch": t_hpr, "bound": "fp64 / ALU issue + per-cloud load balance (ncu: 77% issue-active, "
+                        "0.1% of DRAM bandwidth)", "compulsory_bytes_per_launch": hpr_bytes,
+                        "gbs_on_compulsory_bytes": hpr_bytes / (t_hpr * 1e-3) / 1e9,
+                        "clouds_per_s": 2 * B / (t_hpr * 1e-3)}
     ms = total_ms / args.steps
     return {
         "metric": TRAIN_METRIC, "value": B * world / (ms * 1e-3), "unit": "segments/s", "n_gpus": world,
@@ -423,7 +458,7 @@ def run_ours_train(args, rank, world, local_rank):
                                        ("; batch i+1 is synthesized next to the train step of batch i (prefetch 1, "
                                         "as tf.data prefetch(1) in the reference)" if pipelined else ""),
                                        "l2": "per-step working set (~0.5 GB of activations) exceeds the 126 MB L2; no flush"}),
-        "roofline": roofline,
+        "roofline": roofline, "synthesis_kernel": synthesis_kernel,
         "stage_ms": {"synthesis": t_syn, "train_step_total": ms},
         "losses_last_step": losses,
         "e2e": {"value": B * world / (e2e_s / args.steps), "unit": "segments/s", "h2d_bytes_per_step": h2d,

@@ -13,6 +13,7 @@ fp32 gradient buffer per step followed by a 1/world scale inside the Adam kernel
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -58,6 +59,8 @@ class CloudAAETrainer:
         self.d_rot = torch.empty(B, 3, **f32); self.d_trans = torch.empty(B, 3, **f32)
         self.trans_pred = torch.empty(B, 3, **f32)
         self.losses = torch.zeros(4, **f32)  # total, chamfer, trans, rot
+        self._loss_stream = torch.cuda.Stream(self.dev, priority=-1) if self.engine.concurrent else None
+        self._loss_pending = False
         self._graph = None
         self._static = None
         self.launches_per_step = 0
@@ -96,9 +99,22 @@ class CloudAAETrainer:
         self._c("caae_add_cloud_vec", B, M, p(recon), p(self.mean), p(self.recon))
         self._c("caae_nn_distance", B, M, p(self.recon), M, p(target), p(self.dist1), p(self.idx1), p(self.dist2),
                 p(self.idx2))
-        self._c("caae_loss_reduce", B * M, p(self.dist1), p(self.dist2), B, p(self.per_trans), p(self.per_rot),
-                p(self.losses))
+        # the reported loss values feed nothing downstream: reduce them next to the backward pass
+        side = self._loss_stream
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            self._loss_pending = True
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            self._c("caae_loss_reduce", B * M, p(self.dist1), p(self.dist2), B, p(self.per_trans), p(self.per_rot),
+                    p(self.losses))
+        if not start_heads_backward:
+            self._join_loss()
         return self.losses
+
+    def _join_loss(self):
+        if self._loss_pending:
+            torch.cuda.current_stream(self.dev).wait_stream(self._loss_stream)
+            self._loss_pending = False
 
     def backward(self, target):
         B, M = self.B, self.M
@@ -109,6 +125,7 @@ class CloudAAETrainer:
 
     def apply_gradients(self):
         p = _Engine._p
+        self._join_loss()
         if self.world > 1:
             self.reducer.start(0)
             self.reducer.finish()
