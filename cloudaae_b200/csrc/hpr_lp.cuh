@@ -213,7 +213,8 @@ HPR_HD int lp_lane(const View& h, int self, const Seq& seq, double& sa_out, doub
 HPR_HD float verify_disk2(float saf, float sbf, float fz, float fzmax, float kh) {
   const float s2 = (saf * saf + sbf * sbf) * 1.0002f;
   const float dw = (fzmax - fz) + 2e-6f * (fabsf(fzmax) + fabsf(fz)) + 1e-12f;
-  return (dw + s2 / (4.f * kh) * 1.0001f) / kh * 1.001f;
+  const float ikh = 1.0f / kh;   // loop-invariant for the caller; the 1.0001 / 1.001 factors absorb the extra rounding
+  return (dw + s2 * (0.25f * ikh) * 1.0001f) * ikh * 1.001f;
 }
 
 // Cell of sorted position p: the largest c with cell_start[c] <= p.
