@@ -80,6 +80,7 @@ _SIGNATURES = {k: [_CODES[c] for c in v] for k, v in _SIGNATURES.items()}
 _SPECIAL = {
     "caae_abi_version": ([], _int),
     "caae_status_string": ([_int], ctypes.c_char_p),
+    "caae_crc32c": ([ctypes.c_uint, _ptr, ctypes.c_ulonglong], ctypes.c_uint),
     "caae_fps_scratch_bytes": ([_int, _int], ctypes.c_size_t),
     "caae_edge_parts": ([_int, _int, _int, _int, _int], _int),
     "caae_col_parts": ([_int], _int),

@@ -39,6 +39,9 @@ typedef void* caae_stream_t; /* cudaStream_t */
 int caae_abi_version(void);
 /* Human-readable text for a status returned by any entry point (static storage). */
 const char* caae_status_string(int status);
+/* Host utility: CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start) — the per-tensor
+ * checksum of the tf.train.Saver checkpoint format (train_cloudAAE_ycbv.py:276). */
+unsigned int caae_crc32c(unsigned int crc, const void* data, unsigned long long n);
 
 /* ---- sampling ops -------------------------------------------------------------------------- */
 

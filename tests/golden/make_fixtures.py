@@ -7,6 +7,9 @@ Writes
   tests/golden/ycb_models_xyz.npy   float32 [21,2048,3]  (xyz columns of obj_models.tfrecords)
   tests/golden/ycb_poses.npz        translation f32[21*P,3], axisangle f32[21*P,3], class_id i64[21*P]
                                     = the first P=256 records of every <cls>_syn.tfrecords
+  tests/golden/ref_model.ckpt.index the TensorBundle index of the reference's shipped network snapshot
+                                    (trained_network/20200908-204328/model.ckpt.index, 6.6 KB; names, shapes and
+                                    offsets only — the reference does not ship the tensor data)
 The GPU box has no /root/reference, so tests and bench.py read these instead.
 """
 import os
@@ -37,6 +40,9 @@ def main():
     np.savez(os.path.join(HERE, "ycb_poses.npz"), translation=np.concatenate(ts),
              axisangle=np.concatenate(axs), class_id=np.concatenate(cs), total_records=np.int64(total))
     print("models", models.shape, "poses kept", sum(map(len, cs)), "of", total)
+    import shutil
+    shutil.copyfile(os.path.join(REF, "trained_network/20200908-204328/model.ckpt.index"),
+                    os.path.join(HERE, "ref_model.ckpt.index"))
 
 
 if __name__ == "__main__":
