@@ -78,6 +78,8 @@ def _header_prototypes():
                     codes += "i"
                 elif a.startswith("unsigned long long "):
                     codes += "Q"
+                elif a.startswith("unsigned int "):
+                    codes += "I"
                 elif a.startswith("long "):
                     codes += "l"
                 elif a.startswith("float "):
