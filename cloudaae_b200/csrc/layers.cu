@@ -507,44 +507,64 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
   __syncthreads();
 
   const float invk = 1.f / (float)k;
+  static_assert(ES_CH == 64, "a lane owns the channel pair (2 tx, 2 tx + 1) of the 64-channel slice");
+  {
+    // one lane = two adjacent channels: the neighbour index is loaded once per pair and the gather is one LDS.64
+    const int cl = 2 * tx, ch = c0 + cl;
+    float sc[2] = {0.f, 0.f}, sh[2] = {0.f, 0.f}, mu[2] = {0.f, 0.f}, is[2] = {0.f, 0.f};
+    float mdy[2] = {0.f, 0.f}, mdz[2] = {0.f, 0.f}, gis[2] = {0.f, 0.f};
 #pragma unroll
-  for (int h = 0; h < ES_CH / 32; ++h) {
-    const int cl = tx + 32 * h, ch = c0 + cl;
-    float sc = 0.f, sh = 0.f, mu = 0.f, is = 0.f, mdy = 0.f, mdz = 0.f, gis = 0.f;
-    if (MODE >= 1) { sc = scale[ch]; sh = shift[ch]; }
-    if (MODE >= 2) { mu = mean[ch]; is = invstd[ch]; }
-    if (MODE == 3) { mdy = coef[ch]; mdz = coef[cout + ch]; gis = coef[2 * cout + ch]; }
-    double a = 0.0, b = 0.0;
+    for (int c = 0; c < 2; ++c) {
+      if (MODE >= 1) { sc[c] = scale[ch + c]; sh[c] = shift[ch + c]; }
+      if (MODE >= 2) { mu[c] = mean[ch + c]; is[c] = invstd[ch + c]; }
+      if (MODE == 3) { mdy[c] = coef[ch + c]; mdz[c] = coef[cout + ch + c]; gis[c] = coef[2 * cout + ch + c]; }
+    }
+    double a[2] = {0.0, 0.0}, b[2] = {0.0, 0.0};
     for (int p = ty; p < n; p += 32) {
-      const float pv = PQ[(base + p) * ldpq + ch];
-      float g = 0.f, acc = 0.f;
-      if (MODE >= 2) g = dOut[(base + p) * lddo + ch] * invk;
+      const float2 pv2 = *reinterpret_cast<const float2*>(PQ + (base + p) * ldpq + ch);
+      const float pv[2] = {pv2.x, pv2.y};
+      float g[2] = {0.f, 0.f}, acc[2] = {0.f, 0.f};
+      if (MODE >= 2) {
+        const float* gp = dOut + (base + p) * lddo + ch;   // (a slice of a wider buffer: no alignment assumed)
+        g[0] = gp[0] * invk; g[1] = gp[1] * invk;
+      }
       const int* nb = s_idx + p * k;
       // sums over the k neighbours of ONE point in fp32 (k terms), across points in fp64: the fp32->fp64
       // conversions and DADDs per neighbour were the bottleneck of the two reduction passes
-      float fa = 0.f, fb = 0.f;
+      float fa[2] = {0.f, 0.f}, fb[2] = {0.f, 0.f};
       for (int j = 0; j < k; ++j) {
         const int q = nb[j];
-        const float z = pv + Qs[q * ES_CH + cl];
-        if (MODE == 0) {
-          fa += z; fb = fmaf(z, z, fb);
-        } else if (MODE == 1) {
-          acc += fmaxf(fmaf(z, sc, sh), 0.f);
-        } else if (MODE == 2) {
-          if (fmaf(z, sc, sh) > 0.f) { fa += 1.f; fb += (z - mu) * is; }
-        } else {
-          const float dy = (fmaf(z, sc, sh) > 0.f) ? g : 0.f;
-          const float dz = gis * (dy - mdy - (z - mu) * is * mdz);
-          acc += dz;
-          atomicAdd(dQs + q * ES_CH + cl, dz);
+        const float2 q2 = *reinterpret_cast<const float2*>(Qs + q * ES_CH + cl);
+        const float qv[2] = {q2.x, q2.y};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float z = pv[c] + qv[c];
+          if (MODE == 0) {
+            fa[c] += z; fb[c] = fmaf(z, z, fb[c]);
+          } else if (MODE == 1) {
+            acc[c] += fmaxf(fmaf(z, sc[c], sh[c]), 0.f);
+          } else if (MODE == 2) {
+            if (fmaf(z, sc[c], sh[c]) > 0.f) { fa[c] += 1.f; fb[c] += (z - mu[c]) * is[c]; }
+          } else {
+            const float dy = (fmaf(z, sc[c], sh[c]) > 0.f) ? g[c] : 0.f;
+            const float dz = gis[c] * (dy - mdy[c] - (z - mu[c]) * is[c] * mdz[c]);
+            acc[c] += dz;
+            atomicAdd(dQs + q * ES_CH + cl + c, dz);
+          }
         }
       }
-      if (MODE == 0) { a += (double)fa; b += (double)fb; }
-      if (MODE == 2) { a += (double)(g * fa); b += (double)(g * fb); }
-      if (MODE == 1) out[(base + p) * ldo + ch] = acc * invk;
-      if (MODE == 3) out[(base + p) * ldo + ch] = acc;  // dP
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (MODE == 0) { a[c] += (double)fa[c]; b[c] += (double)fb[c]; }
+        if (MODE == 2) { a[c] += (double)(g[c] * fa[c]); b[c] += (double)(g[c] * fb[c]); }
+      }
+      if (MODE == 1) { float* op = out + (base + p) * ldo + ch; op[0] = acc[0] * invk; op[1] = acc[1] * invk; }
+      if (MODE == 3) *reinterpret_cast<float2*>(out + (base + p) * ldo + ch) = make_float2(acc[0], acc[1]);  // dP
     }
-    if (MODE == 0 || MODE == 2) { s_a[ty][cl] = a; s_b[ty][cl] = b; }
+    if (MODE == 0 || MODE == 2) {
+      s_a[ty][cl] = a[0]; s_b[ty][cl] = b[0];
+      s_a[ty][cl + 1] = a[1]; s_b[ty][cl + 1] = b[1];
+    }
   }
   if (MODE == 0 || MODE == 2) {
     __syncthreads();
