@@ -319,6 +319,39 @@ bn_act_pool_kernel(int group, int C, const float* __restrict__ Y, int ld, const 
   }
 }
 
+// float4 variant of the mean pool (C % 128 == 0, 16-byte aligned rows): block (32, 8) = 128 channels x 8 row lanes,
+// four independent 16-byte loads in flight per thread
+__global__ void __launch_bounds__(256)
+bn_act_meanpool_vec4_kernel(int group, int C, const float* __restrict__ Y, int ld, const float* __restrict__ scale,
+                            const float* __restrict__ shift, float* __restrict__ emb) {
+  __shared__ float4 s_v[8][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * 128 + tx * 4, g = blockIdx.y;
+  const float4 sc = *reinterpret_cast<const float4*>(scale + ch), sh = *reinterpret_cast<const float4*>(shift + ch);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* base = Y + (size_t)g * group * ld + ch;
+  for (int r = ty; r < group; r += 32) {
+    float4 y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      y[u] = (r + 8 * u < group) ? *reinterpret_cast<const float4*>(base + (size_t)(r + 8 * u) * ld) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r + 8 * u >= group) break;
+      acc.x += fmaxf(fmaf(y[u].x, sc.x, sh.x), 0.f); acc.y += fmaxf(fmaf(y[u].y, sc.y, sh.y), 0.f);
+      acc.z += fmaxf(fmaf(y[u].z, sc.z, sh.z), 0.f); acc.w += fmaxf(fmaf(y[u].w, sc.w, sh.w), 0.f);
+    }
+  }
+  s_v[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int r = 1; r < 8; ++r) { const float4 o = s_v[r][tx]; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    const float inv = 1.f / (float)group;
+    *reinterpret_cast<float4*>(emb + (size_t)g * C + ch) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+}
+
 // dY = gamma*invstd*(dy - mdy - yhat*mdyz) (training BN) — may run in place (dY == Y)
 __global__ void __launch_bounds__(256)
 bn_act_bwd_kernel(long total, int C, const float* Y, int ld, const float* __restrict__ scale,
@@ -384,6 +417,9 @@ col_reduce_vec4_kernel(int R, int C, const float* __restrict__ Y, int ld, const 
     float4 y[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) y[u] = (r + 8 * u < r1) ? ld4(Y + (size_t)(r + 8 * u) * ld + ch) : make_float4(0, 0, 0, 0);
+    // (MODE 1: the four rows of a batch are summed in fp32 before they join the fp64 accumulators — the
+    // fp32->fp64 conversions per element, not HBM, bounded this pass)
+    float fa[4] = {0.f, 0.f, 0.f, 0.f}, fb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int rr = r + 8 * u;
@@ -407,9 +443,13 @@ col_reduce_vec4_kernel(int R, int C, const float* __restrict__ Y, int ld, const 
         for (int c = 0; c < 4; ++c) {
           bool on = !relu || fmaf(yv[c], scv[c], shv[c]) > 0.f;
           if (argmax != nullptr) on = on && (am[c] == rr - gr * group);
-          if (on) { a[c] += (double)gv[c]; b[c] += (double)gv[c] * (double)((yv[c] - muv[c]) * isv[c]); }
+          if (on) { fa[c] += gv[c]; fb[c] = fmaf(gv[c], (yv[c] - muv[c]) * isv[c], fb[c]); }
         }
       }
+    }
+    if (MODE == 1) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { a[c] += (double)fa[c]; b[c] += (double)fb[c]; }
     }
   }
 #pragma unroll
@@ -764,6 +804,11 @@ extern "C" int caae_bn_act_pool(int groups, int group, int C, const float* Y, in
   CAAE_RETURN_IF(groups <= 0 || group <= 0 || C <= 0 || ld < C || groups > 65535, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!Y || !scale || !shift || !emb, CAAE_E_NULLPTR);
   dim3 grid((C + 31) / 32, groups), block(32, 8);
+  if (!maxpool && C % 128 == 0 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(emb) |
+                                                   reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0) {
+    bn_act_meanpool_vec4_kernel<<<dim3(C / 128, groups), block, 0, as_stream(stream)>>>(group, C, Y, ld, scale, shift, emb);
+    return CAAE_LAUNCH_STATUS();
+  }
   if (maxpool) bn_act_pool_kernel<true><<<grid, block, 0, as_stream(stream)>>>(group, C, Y, ld, scale, shift, emb, argmax);
   else bn_act_pool_kernel<false><<<grid, block, 0, as_stream(stream)>>>(group, C, Y, ld, scale, shift, emb, argmax);
   return CAAE_LAUNCH_STATUS();

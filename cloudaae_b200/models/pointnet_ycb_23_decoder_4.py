@@ -194,14 +194,27 @@ class _Engine:
             ("pn_fc1_decoder", "pn_fc2_decoder", "pn_output")
         self.branches = [[fc1, fc2, out], [f"{p}_rot_fc1", f"{p}_rot_fc2", f"{p}_output_rot"],
                          [f"{p}_trans_fc1", f"{p}_trans_fc2", f"{p}_output_trans"]]
+        # The FC GEMMs are split-K (M = batch): their outputs accumulate into zero-filled buffers.  All of them
+        # live in ONE flat buffer that a single fill kernel clears off the critical path (side stream, start of
+        # forward) instead of one zero-fill launch in front of every GEMM of the chain.
         self.fc_y, self.fc_a, self.fc_d = {}, {}, {}
+        n_acc = sum(B * self.scopes[s][1] * (2 if self.scopes[s][2] else 1) for br in self.branches for s in br) + 3 * B * 1024
+        self.fc_acc_flat = torch.zeros(n_acc, **f32)
+        off = 0
+
+        def _take(rows, cols):
+            nonlocal off
+            t = self.fc_acc_flat[off:off + rows * cols].view(rows, cols)
+            off += rows * cols
+            return t
+
         for br in self.branches:
             for s in br:
                 fout = self.scopes[s][1]
-                self.fc_y[s] = torch.empty(B, fout, **f32)
+                self.fc_y[s] = _take(B, fout)
                 if self.scopes[s][2]:
                     self.fc_a[s] = torch.empty(B, fout, **f32)
-                    self.fc_d[s] = torch.empty(B, fout, **f32)
+                    self.fc_d[s] = _take(B, fout)
         self.x0 = None
         self.trained = (False, False)
         self.after_fc_backward = None
@@ -214,7 +227,7 @@ class _Engine:
         self.s_branch = [torch.cuda.Stream(**hi) for _ in range(2)] if self.concurrent else []
         self.s_wgrad = [torch.cuda.Stream(**hi) for _ in range(3)] if self.concurrent else []
         self.s_enc = torch.cuda.Stream(**hi) if self.concurrent else None
-        self.d_emb_br = torch.empty(3, B, 1024, **f32)
+        self.d_emb_br = _take(3 * B, 1024).view(3, B, 1024)
         self._heads_pending = False
 
     # -- helpers
@@ -244,7 +257,7 @@ class _Engine:
         fin, fout, has_bn = self.scopes[scope]
         B, v = self.B, self.v
         y = self.fc_y[scope]
-        self._gemm(0, 0, B, fout, fin, x, fin, v[f"{scope}/weights"], fout, y, fout, v[f"{scope}/biases"])
+        self._gemm(0, 0, B, fout, fin, x, fin, v[f"{scope}/weights"], fout, y, fout, v[f"{scope}/biases"], 1)
         if not has_bn:
             return None
         bn, a = self.bn[scope], self.fc_a[scope]
@@ -280,19 +293,19 @@ class _Engine:
         if w is not None: self._fork(w)
         with self._on(w):
             self._dense_wgrad(s3, self.fc_a[s2], f3[0], B, d_out, True)
-        self._gemm(0, 1, B, f3[0], f3[1], d_out, f3[1], self.v[f"{s3}/weights"], f3[1], d2, f3[0])
+        self._gemm(0, 1, B, f3[0], f3[1], d_out, f3[1], self.v[f"{s3}/weights"], f3[1], d2, f3[0], None, 1)
         # fc2: BN+ReLU backward, wgrad, dgrad
         self._fc_bn_bwd(s2, d2)
         if w is not None: self._fork(w)
         with self._on(w):
             self._dense_wgrad(s2, self.fc_a[s1], f2[0], B, d2, False)
-        self._gemm(0, 1, B, f2[0], f2[1], d2, f2[1], self.v[f"{s2}/weights"], f2[1], d1, f2[0])
+        self._gemm(0, 1, B, f2[0], f2[1], d2, f2[1], self.v[f"{s2}/weights"], f2[1], d1, f2[0], None, 1)
         # fc1
         self._fc_bn_bwd(s1, d1)
         if w is not None: self._fork(w)
         with self._on(w):
             self._dense_wgrad(s1, self.emb, f1[0], B, d1, False)
-        self._gemm(0, 1, B, f1[0], f1[1], d1, f1[1], self.v[f"{s1}/weights"], f1[1], self.d_emb_br[bi], f1[0])
+        self._gemm(0, 1, B, f1[0], f1[1], d1, f1[1], self.v[f"{s1}/weights"], f1[1], self.d_emb_br[bi], f1[0], None, 1)
         if w is not None: self._join(w)
 
     def backward_heads_async(self, d_rot, d_trans):
@@ -377,10 +390,12 @@ class _Engine:
         self.x0 = x
         self.trained = (train_enc, train_fc)
         before = None
+        se = self.s_enc
+        if se is not None: self._fork(se)
+        with self._on(se):   # accumulation targets of the FC stack's split-K GEMMs (forward and backward)
+            self._c("caae_fill_f32", self.fc_acc_flat.numel(), self._p(self.fc_acc_flat), 0.0)
         if self.model == "dgcnn":
             feat, ldf, cknn = x, D, 3
-            se = self.s_enc
-            if se is not None: self._fork(se)
             with self._on(se):   # the folded weights depend on the parameters only
                 for l in range(4):
                     self._c("caae_edge_fold_weights", self.cins[l], self.couts[l], self._p(self.v[f"dgcnn{l + 1}/weights"]),
@@ -422,6 +437,7 @@ class _Engine:
             bn = self.bn[self.enc[-1]]
             self._c("caae_bn_act_pool", B, N, 1024, self._p(self.enc_y[-1]), 1024, self._p(bn["scale"]),
                     self._p(bn["shift"]), 1, self._p(self.emb), self._p(self.argmax))
+        if se is not None: self._join(se)
         self.forward_fc(train_fc, decay)
         outs = [self.fc_y[br[-1]] for br in self.branches]
         return outs[0], outs[1], outs[2], self.emb, before
