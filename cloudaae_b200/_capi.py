@@ -75,6 +75,11 @@ _SIGNATURES = {
     "caae_synth_points": "iiippppppffffppp" "p",
     "caae_hpr_select": "iippiipppp" "p",
     "caae_hpr_select_pair": "iipipppipippppi" "p",
+    # real-segment front end of evaluation, ICP refinement
+    "caae_segment_extract": "iiiippppppipppppp" "p",
+    "caae_radius_outlier": "iippidippp" "p",
+    "caae_fps_seeded_f64": "iiipppppp" "p",
+    "caae_icp_refine": "iiippippddiiddpppp".replace(" ", "") + "p",
 }
 _SIGNATURES = {k: [_CODES[c] for c in v] for k, v in _SIGNATURES.items()}
 _SPECIAL = {

@@ -217,6 +217,48 @@ int caae_hpr_select_pair(int b, int n_a, const float* flipped_a, int take_a, con
                          const float* pad_uniform_b, float* out_pts_b, int* num_vis_b, const float* org,
                          int org_stride_pts, caae_stream_t stream);
 
+/* ==== real-segment front end of evaluation =====================================
+ * evaluate_cloudAAE_ycbv.py:164-178 (get_pointcloud), :262-272 (segment_not_empty), :219-223
+ * (segment_mean_distance_filter), :250-258 (get_outlier_idx: open3d remove_radius_outlier), :230-247
+ * (FPS_random).  A "segment" is one (frame, class) pair; every entry point works on nseg segments at once. */
+
+/* depth u16[nframes,h,w], label u8[nframes,h,w] (one-based class labels), intrinsics f32[nframes,5] =
+ * {fx, fy, cx, cy, factor_depth}, threshold_per_class f32[num_class] (metres from the segment mean).
+ * Per segment s (frame_of_seg[s], class_of_seg[s]): the camera-frame points of the pixels with
+ * label-1 == class and depth != 0, in pixel order -> xyz_org f32[nseg,cap,3] (optional), n_org i32[nseg]
+ * (optional); those of them within the threshold of their mean -> xyz_filt f32[nseg,cap,3], their pixel
+ * index pix_filt i32[nseg,cap] (optional, for gathering rgb), n_filt i32[nseg]; seg_mean f32[nseg,3]
+ * (optional).  Counts are the true counts; rows past `cap` are dropped.  fp32, one rounding per TF op. */
+int caae_segment_extract(int nseg, int nframes, int h, int w, const int* frame_of_seg, const int* class_of_seg,
+                         const unsigned short* depth, const unsigned char* label, const float* intrinsics,
+                         const float* threshold_per_class, int cap, float* xyz_org, int* n_org, float* xyz_filt,
+                         int* pix_filt, int* n_filt, float* seg_mean, caae_stream_t stream);
+
+/* open3d remove_radius_outlier: point i of segment s (xyz f32[nseg,cap,3], first n_pts[s] rows valid) is an
+ * inlier when more than nb_points points (itself included) lie at squared distance < radius^2 (fp64).
+ * inlier_idx i32[nseg,cap] = inlier ids ascending (tail zero-filled), n_inlier i32[nseg]; when fewer than
+ * min_keep inliers remain every point is kept (evaluate...:256-257).  flag u8[nseg,cap] is scratch. */
+int caae_radius_outlier(int nseg, int cap, const float* xyz, const int* n_pts, int nb_points, double radius,
+                        int min_keep, unsigned char* flag, int* inlier_idx, int* n_inlier, caae_stream_t stream);
+
+/* FPS_random: farthest point sampling in float64 starting from first_idx[s] (the reference draws it with
+ * random.randint), np.argmax tie rule (first maximum).  xyz f32[nseg,cap,3], n_pts i32[nseg], temp
+ * f64[nseg,cap] scratch -> out_idx i32[nseg,k], out_xyz f32[nseg,k,3] (optional). */
+int caae_fps_seeded_f64(int nseg, int cap, int k, const float* xyz, const int* n_pts, const int* first_idx,
+                        double* temp, int* out_idx, float* out_xyz, caae_stream_t stream);
+
+/* ==== ICP refinement of the predicted pose ======================================
+ * evaluate_cloudAAE_ycbv.py:606-624: `outer` calls of open3d registration_icp (point-to-point, at most
+ * max_iter iterations each, stop when fitness and inlier_rmse both change by less than rel_*), the
+ * correspondence radius multiplied by radius_decay after every call.  source f32[nsrc,ns,src_stride]
+ * (first 3 floats of a row = xyz; source_of_seg i32[b] picks the row block, NULL = segment index),
+ * target f32[b,nt,3], T_init f64[b,16] row-major 4x4 -> T_out f64[b,16], fitness f64[b], inlier_rmse
+ * f64[b], iterations i32[b] (last three optional).  One CTA per segment, one launch for everything. */
+int caae_icp_refine(int b, int ns, int src_stride, const float* source, const int* source_of_seg, int nt,
+                    const float* target, const double* T_init, double radius, double radius_decay, int outer,
+                    int max_iter, double rel_fitness, double rel_rmse, double* T_out, double* fitness,
+                    double* inlier_rmse, int* iterations, caae_stream_t stream);
+
 /* Diagnostics (synchronous): copies the per-CTA phase timing of the LAST caae_hpr_select launch into
  * host_buf i64[512][8] = clock64 deltas {set-up, neighbourhood LPs, first verification, later rounds,
  * compaction + selection}, survivors, rounds, slots re-solved in round 0. */
