@@ -180,37 +180,6 @@ def icp_refine(source, target, init, radius=0.01, radius_decay=0.9, outer=10, ma
     return T, fit, rmse, iters
 
 
-# ---- synthetic YCB-Video-shaped frames (there is no real frame in the reference tree) ---------------
-
-def render_frame(clouds, class_ids, h=480, w=640, intrinsics=YCBV_INTRINSICS, splat=2, seed=0, n_stray=300):
-    """Project posed object clouds (camera frame, metres) into a u16 depth image and a u8 label image
-    (one-based labels, nearest surface wins), each point splatted over (2*splat+1)^2 pixels; every pixel
-    gets a background depth; `n_stray` isolated pixels per object carry its label at a wrong depth so both
-    filters have something to remove."""
-    rng = np.random.default_rng(seed)
-    fx, fy, cx, cy, factor = [float(v) for v in intrinsics]
-    zbuf = np.full((h, w), np.inf)
-    label = np.zeros((h, w), np.uint8)
-    for pts, c in zip(clouds, class_ids):
-        u = np.rint(pts[:, 0] * fx / pts[:, 2] + cx).astype(int)
-        v = np.rint(pts[:, 1] * fy / pts[:, 2] + cy).astype(int)
-        tmp = np.full((h, w), np.inf)
-        for du in range(-splat, splat + 1):
-            for dv in range(-splat, splat + 1):
-                uu, vv = u + du, v + dv
-                ok = np.flatnonzero((uu >= 0) & (uu < w) & (vv >= 0) & (vv < h))
-                ok = ok[np.argsort(-pts[ok, 2], kind="stable")]  # far first: the nearest write lands last
-                near = pts[ok, 2] < tmp[vv[ok], uu[ok]]
-                ok = ok[near]
-                tmp[vv[ok], uu[ok]] = pts[ok, 2]
-        m = tmp < zbuf
-        zbuf[m] = tmp[m]
-        label[m] = c + 1
-        ys, xs = rng.integers(0, h, n_stray), rng.integers(0, w, n_stray)
-        zbuf[ys, xs] = float(pts[:, 2].mean()) + rng.uniform(-0.6, 0.6, n_stray)
-        label[ys, xs] = c + 1
-    depth = np.where(np.isfinite(zbuf), zbuf, 2.5)
-    depth_u16 = np.clip(np.rint(depth * factor), 0, 65535).astype(np.uint16)
-    holes = rng.random((h, w)) < 0.02  # invalid depth readings
-    depth_u16[holes] = 0
-    return depth_u16, label
+# synthetic YCB-Video-shaped frames (there is no real frame in the reference tree): the generator is a
+# data helper of the package, shared by the tests and bench.py
+from cloudaae_b200.data.synthetic_frames import render_frame  # noqa: E402,F401
