@@ -11,6 +11,8 @@ exactly what SURVEY.md §8(e) calls for:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -44,7 +46,10 @@ class BucketedAllReduce:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = flat_grad.is_cuda
-        self.side = torch.cuda.Stream(flat_grad.device) if self.cuda else None
+        # the collective outranks everything: at the default (low) priority its CTAs would queue behind the
+        # not-yet-dispatched CTAs of the synthesis branch of a pipelined graph and the exchange would start late
+        prio = int(os.environ.get("CLOUDAAE_NCCL_PRIORITY", "-2"))
+        self.side = torch.cuda.Stream(flat_grad.device, priority=prio) if self.cuda else None
         self._pending = []
 
     def start(self, bucket: int) -> None:
