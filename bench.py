@@ -330,8 +330,9 @@ def run_ours_train(args, rank, world, local_rank):
     pool_d = [{k: torch.from_numpy(v).to(dev) for k, v in bt.items()} for bt in pool_h]
     # one CUDA graph per step; by default the synthesis of batch i+1 runs as a parallel branch next to the
     # train step of batch i (the reference's tf.data prefetch(1), train_cloudAAE_ycbv.py:115)
-    pipelined = os.environ.get("CLOUDAAE_PIPELINE", "1") != "0"
-    capture = tr.capture_online_pipelined if pipelined else tr.capture_online
+    mode = os.environ.get("CLOUDAAE_PIPELINE", "1")
+    pipelined = mode != "0"
+    capture = {"0": tr.capture_online, "1": tr.capture_online_pipelined}.get(mode, tr.capture_online_decoupled)
     static = capture(syn, *[pool_d[0][k] for k in TRAIN_KEYS])
 
     def load(i, src):  # refresh the graph's static pose records
@@ -351,6 +352,7 @@ def run_ours_train(args, rank, world, local_rank):
     s.record()
     for i in range(args.steps):
         load(i, pool_d); tr.replay()
+    tr.join()   # decoupled pipeline: the synthesis running ahead on its own stream ends inside the timed region
     e.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -455,7 +457,10 @@ def run_ours_train(args, rank, world, local_rank):
         "data": "synthetic: committed YCB model fixture x fixture pose records, Philox occluders/noise, random-init weights",
         "config": train_config(world, {"cuda_graph": True,
                                        "synthesis": "on-line, inside the timed step" +
-                                       ("; batch i+1 is synthesized next to the train step of batch i (prefetch 1, "
+                                       ("; two CUDA graphs on two streams with a 2-slot hand-over queue: the synthesis "
+                                        "enqueued by step i feeds step i+2 (parallel map + prefetch in the reference)"
+                                        if mode not in ("0", "1") else
+                                        "; batch i+1 is synthesized next to the train step of batch i (prefetch 1, "
                                         "as tf.data prefetch(1) in the reference)" if pipelined else ""),
                                        "l2": "per-step working set (~0.5 GB of activations) exceeds the 126 MB L2; no flush"}),
         "roofline": roofline, "synthesis_kernel": synthesis_kernel,

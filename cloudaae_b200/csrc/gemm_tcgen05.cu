@@ -66,6 +66,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// TMA store of a shared-memory box (written in the tensor map's swizzle) to global memory; bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -120,11 +135,12 @@ struct GemmParams {
   int atomic;       // split-K: reduce with red.global.add
   int a_mn, b_mn;   // operand majors (0 = K-major, 1 = MN-major)
   uint32_t idesc;
+  int tma_store;    // 128 x 128 kernel: write C with TMA bulk stores from a swizzled staging box (map_c valid)
 };
 
 __global__ void __launch_bounds__(TTHREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   __shared__ __align__(16) float s_bias[TBN];
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-byte alignment
@@ -213,6 +229,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int sbuf = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < TBN; c0 += 32) {
       uint32_t r[32];
@@ -222,6 +239,33 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (p.tma_store) {
+        // every MMA has completed (tmem_full), so the operand stages are free: the A stages become the staging
+        // boxes (two 32-row x 128-byte SWIZZLE_128B boxes per epilogue warp) of one TMA store per chunk —
+        // full 128-byte lines instead of 16 bytes to 32 different lines per STG.128; rows past M are clipped
+        if (n0 + c0 < p.N) {
+          const uint32_t box = smem_a + (uint32_t)(warp - 2) * 8192u + (uint32_t)sbuf * 4096u;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          const uint32_t rowaddr = box + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+            const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            st_shared_v4(rowaddr + (uint32_t)(((j >> 2) ^ (lane & 7)) << 4), v);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_c, box, n0 + c0, m0 + quad * 32);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        }
+        continue;
       }
       if (row < p.M) {
         float* crow = p.C + (size_t)row * p.ldc + n0 + c0;
@@ -258,6 +302,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();   // the staging boxes must outlive the stores reading them
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -461,9 +506,11 @@ gemm_tf32_big_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // while the TMA and MMA warps run the main loop of tile i+1, so the output stream — the real bound of a
 // K = 320 GEMM with a 134 MB result — overlaps the tensor work instead of following it.  Barrier set-up,
 // TMEM allocation and descriptor fetch happen once per CTA.  K-major A; B either major; no split-K.
-constexpr int PS_STAGES = 4;
+constexpr int PS_STAGES = 3;
 constexpr uint32_t PS_STAGE_A = 2 * TSTAGE_A, PS_STAGE_B = TSTAGE_B;
-constexpr uint32_t PS_SMEM = PS_STAGES * (PS_STAGE_A + PS_STAGE_B) + 1024 + 256;
+// epilogue staging: per epilogue warp two 32-row x 128-byte boxes (SWIZZLE_128B, the layout the C tensor map expects)
+constexpr uint32_t PS_STG_BOX = 32 * 128, PS_STG_WARP = 2 * PS_STG_BOX, PS_STG = 8 * PS_STG_WARP;
+constexpr uint32_t PS_SMEM = PS_STAGES * (PS_STAGE_A + PS_STAGE_B) + PS_STG + 1024 + 256;
 constexpr int PS_MAXN = 2048;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -472,12 +519,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 __global__ void __launch_bounds__(BIG_THREADS)
 gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         const GemmParams p, const int tiles_m, const int tiles_n) {
+                         const __grid_constant__ CUtensorMap map_c, const GemmParams p, const int tiles_m,
+                         const int tiles_n) {
   __shared__ __align__(16) float s_bias[PS_MAXN];
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = base, smem_b = base + PS_STAGES * PS_STAGE_A;
-  const uint32_t bars = smem_b + PS_STAGES * PS_STAGE_B;
+  const uint32_t stg = smem_b + PS_STAGES * PS_STAGE_B;   // 1024-byte aligned: every stage is a multiple of 1 KB
+  const uint32_t bars = stg + PS_STG;
   const uint32_t full0 = bars, empty0 = bars + 8 * PS_STAGES;
   const uint32_t tfull0 = empty0 + 8 * PS_STAGES, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -561,7 +610,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     // ===== epilogue: eight warps; two per TMEM lane quadrant, splitting the (row block, 32-column chunk) items =====
     const int quad = warp & 3, part = (warp - 2) >> 2;
     constexpr int NC = TBN / 32, NWORK = 2 * NC;
-    int lt = 0;
+    int lt = 0, sbuf = 0;
     for (int id = blockIdx.x; id < tiles; id += gridDim.x, ++lt) {
       const int acc = lt & 1;
       const int m0 = (id / tiles_n) * (2 * TBM), n0 = (id % tiles_n) * TBN;
@@ -571,6 +620,31 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       auto taddr = [&](int w) { return tlane + (uint32_t)((w / NC) * TBN + (w % NC) * 32); };
       auto store_item = [&](uint32_t (&r)[32], int w) {
         const int h = w / NC, c0 = (w % NC) * 32;
+        if (!p.accumulate) {
+          // registers -> swizzled shared-memory box -> one TMA store of 32 rows x 128 bytes (full lines; rows past M
+          // are clipped by the tensor map).  A thread-per-row STG.128 writes 16 bytes to 32 different lines per
+          // instruction: that, not the tensor pipe, bounded this kernel (134 MB at 1.9 TB/s).
+          const uint32_t box = stg + (uint32_t)(warp - 2) * PS_STG_WARP + (uint32_t)sbuf * PS_STG_BOX;
+          if (lane == 0) tma_store_wait_read<1>();   // the store that last read this box (two items ago) is done with it
+          __syncwarp();
+          const uint32_t rowaddr = box + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+            const float4 bv = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + j);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            st_shared_v4(rowaddr + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4), v);   // SWIZZLE_128B: chunk ^= row % 8
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_c, box, n0 + c0, m0 + h * TBM + quad * 32);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+          return;
+        }
         const int row = m0 + h * TBM + quad * 32 + lane;
         if (row >= p.M) return;
         float* crow = p.C + (size_t)row * p.ldc + n0 + c0;
@@ -580,10 +654,8 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                                  __uint_as_float(r[j + 3]));
           const float4 bv = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + j);
           v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-          if (p.accumulate) {
-            const float4 o = *reinterpret_cast<const float4*>(crow + j);
-            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-          }
+          const float4 o = *reinterpret_cast<const float4*>(crow + j);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
           *reinterpret_cast<float4*>(crow + j) = v;
         }
       };
@@ -604,6 +676,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
     }
+    if (lane == 0) tma_store_wait_all();   // the staging boxes must outlive the bulk stores that read them
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -654,6 +727,19 @@ static int make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t
   return r == CUDA_SUCCESS ? 0 : CAAE_E_UNSUPPORTED;
 }
 
+// Output map for TMA-store epilogues: C[outer = rows, inner = columns] fp32, boxes of 32 columns (128 bytes) x 32 rows
+static int make_map_c(CUtensorMap* map, float* ptr, uint64_t cols, uint64_t rows, uint64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return CAAE_E_UNSUPPORTED;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : CAAE_E_UNSUPPORTED;
+}
+
 }  // namespace caae
 
 using namespace caae;
@@ -689,6 +775,7 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
   if (rc) return rc;
 
   GemmParams p;
+  p.tma_store = 0;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
   p.a_mn = transa ? 1 : 0;
   p.b_mn = transb ? 0 : 1;
@@ -715,10 +802,13 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
       if (e != cudaSuccess) return (int)e;
       psattr = true;
     }
+    CUtensorMap map_c2;
+    rc = make_map_c(&map_c2, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc);
+    if (rc) return rc;
     const int tm = (M + 2 * TBM - 1) / (2 * TBM), tn = N / TBN;
     p.kb_per_split = num_kb; p.atomic = 0; p.accumulate = accumulate;
     const int ctas = tm * tn < kNumSMs ? tm * tn : kNumSMs;
-    gemm_tf32_persist_kernel<<<ctas, BIG_THREADS, PS_SMEM, s>>>(map_a2, map_b2, p, tm, tn);
+    gemm_tf32_persist_kernel<<<ctas, BIG_THREADS, PS_SMEM, s>>>(map_a2, map_b2, map_c2, p, tm, tn);
     return CAAE_LAUNCH_STATUS();
   }
   // the three big dgcnn_agg-shaped contractions: large tiles, one CTA per SM (see gemm_tf32_big_kernel)
@@ -796,6 +886,15 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
   }
   dim3 grid(tiles_n, tiles_m, splits);
   CAAE_RETURN_IF(grid.y > 65535 || grid.z > 65535, CAAE_E_BADSHAPE);
-  gemm_tf32_kernel<<<grid, TTHREADS, TSMEM_BYTES, s>>>(map_a, map_b, p);
+  CUtensorMap map_c = map_a;   // placeholder unless the TMA-store epilogue applies
+  static const bool tma_store_enabled = [] { const char* e = getenv("CAAE_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  p.tma_store = 0;
+  if (tma_store_enabled && !p.atomic && !p.accumulate && N % 32 == 0 && ldc % 4 == 0 && M >= 4096 &&
+      (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+    rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
+  gemm_tf32_kernel<<<grid, TTHREADS, TSMEM_BYTES, s>>>(map_a, map_b, map_c, p);
   return CAAE_LAUNCH_STATUS();
 }

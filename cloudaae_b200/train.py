@@ -152,6 +152,8 @@ class CloudAAETrainer:
 
     # ------------------------------------------------------------------ CUDA graph
     def _capture(self, fn, static, warmup):
+        self._replay_fn = None
+        self._join_streams = ()
         snap = (self.v.flat.clone(), self.v.ema.clone(), self.adam_m.clone(), self.adam_v.clone(), self.state.clone())
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -229,6 +231,108 @@ class CloudAAETrainer:
         self._pipeline_keep = (rec, rec_prev, rec_cur, cur, side, synthesizer)
         return out
 
+    def capture_online_decoupled(self, synthesizer, class_id, axisangle, translation, depth: int = 2, warmup: int = 2):
+        """On-line synthesis and training as TWO CUDA graphs on two streams with a `depth`-slot hand-over queue
+        (the reference's parallel map + prefetch, train_cloudAAE_ycbv.py:96-117): `replay()` trains on the oldest
+        queued batch (high-priority stream) and enqueues the synthesis of one new batch from the pose records
+        currently in the static inputs (low-priority stream) into the slot it has just freed.  Unlike the
+        single-graph pipeline there is no barrier at the step boundary: the long tail of the hidden-point-
+        removal kernel (one cloud per CTA, cloud costs spread 5x) runs under the NEXT train step instead of
+        idling the GPU.  Every replay still performs one full synthesis and one full train step.
+        `prime_pipeline(batches)` fills the queue (list of `depth` record tuples; default: the static records)."""
+        B, D = self.B, int(depth)
+        assert D >= 1
+        rec = torch.empty(7 * B, dtype=torch.float32, device=self.dev)   # static inputs: records of the batch to synthesize
+        static = (rec[:B].view(torch.int32), rec[B:4 * B].view(B, 3), rec[4 * B:].view(B, 3))
+        for dst, src in zip(static, (class_id, axisangle, translation)):
+            dst.copy_(src)
+        rec_syn = rec.clone()                                            # what the synthesis graph reads
+        rec_cur = rec.clone()                                            # records of the batch being trained on
+        cur = torch.empty_like(synthesizer.out_flat)
+        slots_x = [torch.empty_like(synthesizer.out_flat) for _ in range(D)]
+        slots_r = [torch.empty_like(rec) for _ in range(D)]
+        n3 = B * self.N * 3
+        cur_vis, cur_tgt, cur_noise = cur[:n3].view(B, self.N, 3), cur[n3:5 * n3].view(B, 4 * self.N, 3), \
+            cur[5 * n3:].view(B, self.N, 3)
+        views = lambda r: (r[:B].view(torch.int32), r[B:4 * B].view(B, 3), r[4 * B:].view(B, 3))  # noqa: E731
+        c_cur, a_cur, t_cur = views(rec_cur)
+        c_syn, a_syn, t_syn = views(rec_syn)
+        s_syn = torch.cuda.Stream(self.dev, priority=0)
+        s_train = torch.cuda.Stream(self.dev, priority=-1)
+        main = torch.cuda.current_stream(self.dev)
+
+        # ---- synthesis graph (low-priority stream)
+        s_syn.wait_stream(main)
+        with torch.cuda.stream(s_syn):
+            for _ in range(warmup):
+                synthesizer.synthesize(c_syn, a_syn, t_syn)
+        main.wait_stream(s_syn)
+        synth_graph = torch.cuda.CUDAGraph()
+        before = _capi.COUNTER[0]
+        with torch.cuda.graph(synth_graph, stream=s_syn):
+            synthesizer.synthesize(c_syn, a_syn, t_syn)
+        synth_launches = _capi.COUNTER[0] - before
+        # ---- train graph (high-priority stream, via the common helper)
+        cur.copy_(synthesizer.out_flat); rec_cur.copy_(rec_syn)
+        self._capture(lambda: self.train_step(cur_vis, cur_tgt, c_cur, t_cur, a_cur, cur_noise), (), warmup)
+        self.launches_per_step += synth_launches
+        st = {"k": 0, "ready": [None] * D, "fresh": True}
+
+        def prime(batches=None):
+            torch.cuda.synchronize(self.dev)
+            for j in range(D):
+                src = static if batches is None else batches[j]
+                for dst, x in zip((c_syn, a_syn, t_syn), src):
+                    dst.copy_(x)
+                synthesizer.synthesize(c_syn, a_syn, t_syn)
+                slots_x[j].copy_(synthesizer.out_flat); slots_r[j].copy_(rec_syn)
+            st["k"], st["ready"], st["fresh"] = 0, [None] * D, True
+
+        def replay():
+            main = torch.cuda.current_stream(self.dev)
+            slot = st["k"] % D
+            if st["fresh"]:                      # the queue was filled on the caller's stream
+                s_train.wait_stream(main)
+                st["fresh"] = False
+            if st["ready"][slot] is not None:
+                s_train.wait_event(st["ready"][slot])
+            with torch.cuda.stream(s_train):
+                cur.copy_(slots_x[slot]); rec_cur.copy_(slots_r[slot])
+                consumed = torch.cuda.Event(); consumed.record(s_train)
+                self._graph.replay()
+                done = torch.cuda.Event(); done.record(s_train)
+            s_syn.wait_stream(main)              # the records the caller has just loaded
+            s_syn.wait_event(consumed)           # the slot is free
+            with torch.cuda.stream(s_syn):
+                rec_syn.copy_(rec)
+                taken = torch.cuda.Event(); taken.record(s_syn)
+                synth_graph.replay()
+                slots_x[slot].copy_(synthesizer.out_flat); slots_r[slot].copy_(rec_syn)
+                ready = torch.cuda.Event(); ready.record(s_syn)
+            st["ready"][slot] = ready
+            main.wait_event(taken)               # the caller may overwrite the static records again
+            main.wait_event(done)                # ... and sees this step's losses / parameters
+            st["k"] += 1
+            return self.losses
+
+        prime()
+        self.prime_pipeline = prime
+        self._replay_fn = replay
+        self._join_streams = (s_syn, s_train)
+        self.pipeline_depth = D
+        self._pipeline_keep = (rec, rec_syn, rec_cur, cur, slots_x, slots_r, s_syn, s_train, synth_graph, synthesizer, st)
+        return static
+
+    def join(self):
+        """Order the caller's stream after everything `replay()` has enqueued so far, including synthesis
+        work still running ahead on the side streams of the decoupled pipeline."""
+        main = torch.cuda.current_stream(self.dev)
+        for s_ in getattr(self, "_join_streams", ()):
+            main.wait_stream(s_)
+
     def replay(self):
+        fn = getattr(self, "_replay_fn", None)
+        if fn is not None:
+            return fn()
         self._graph.replay()
         return self.losses

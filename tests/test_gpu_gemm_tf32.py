@@ -94,3 +94,27 @@ def test_gemm_tf32_persistent_forward_shapes(M, N, K, tb):
     _run(0, tb, M, N, K, A, K, B, B.shape[1], C, N, None, 1)   # C += A B
     torch.cuda.synchronize()
     assert (C[rows].double() - (2 * want - bias.double())).abs().max().item() <= 8e-3 * scale / K ** 0.5
+
+
+@pytest.mark.parametrize("M,N,K,ldc,tb", [(32768, 128, 64, 128, 0), (20001, 256, 64, 320, 0), (4100, 160, 96, 160, 1),
+                                          (32768, 256, 128, 256, 0)])
+def test_gemm_tf32_tma_store_epilogue(M, N, K, ldc, tb):
+    """EdgeConv-projection shapes (tall M, N a multiple of 32, aligned row pitch, no split-K) write C with TMA
+    bulk stores from a swizzled staging box: every element right, ragged last row tile clipped, a partial last
+    column tile (N = 160), columns beyond N of a wider buffer untouched."""
+    g = torch.Generator("cuda").manual_seed(23 + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = (torch.randn(N, K, device="cuda", generator=g) if tb else torch.randn(K, N, device="cuda", generator=g)) * 0.1
+    bias = torch.randn(N, device="cuda", generator=g)
+    C = torch.full((M + 3, ldc), 7.0, device="cuda")
+    _run(0, tb, M, N, K, A, K, B, B.shape[1], C, ldc, bias)
+    torch.cuda.synchronize()
+    Bm = B.T if tb else B
+    ref = A @ Bm + bias
+    scale = (A[:256].abs().double() @ Bm.abs().double()).max().item()
+    assert (C[:M, :N] - ref).abs().max().item() <= 4e-3 * scale
+    assert (C[:M, N:] == 7.0).all() and (C[M:] == 7.0).all()
+    rows = torch.randint(0, M, (128,), device="cuda", generator=g)
+    rows[:3] = torch.tensor([0, 127, M - 1], device="cuda")
+    want = A[rows].double() @ Bm.double() + bias.double()
+    assert (C[rows, :N].double() - want).abs().max().item() <= 4e-3 * scale / K ** 0.5

@@ -202,3 +202,39 @@ def test_pipelined_graph_equals_sequential_steps():
     for w, g in zip(want, got):
         assert torch.allclose(w, g, rtol=1e-2, atol=1e-5), (w, g)
     assert (t_seq.v.flat - t_pipe.v.flat).abs().mean().item() < 1e-4
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_decoupled_two_graph_pipeline_equals_sequential_steps(depth):
+    """capture_online_decoupled (synthesis and training as two graphs on two streams, `depth` batches in
+    flight) must produce the losses of sequential train_step_online calls on the same records and Philox
+    counters: batch k is synthesized by the k-th synthesis call in both."""
+    from cloudaae_b200.train import CloudAAETrainer
+    b, n, steps = 8, 256, 5
+    models = load_models_xyz()
+    batches = []
+    for i in range(steps + depth):
+        cls, ax, tr = _poses(b, 60 + i)
+        batches.append(tuple(torch.from_numpy(x).cuda() for x in (cls, ax, tr)))
+
+    syn = SegmentSynthesizer(models, b, n, seed=3)
+    t_seq = CloudAAETrainer(batch_size=b, num_point=n, seed=1)
+    syn.counter.fill_(100)
+    want = [t_seq.train_step_online(syn, *batches[i]).clone() for i in range(steps)]
+
+    syn2 = SegmentSynthesizer(models, b, n, seed=3)
+    t_dec = CloudAAETrainer(batch_size=b, num_point=n, seed=1)
+    static = t_dec.capture_online_decoupled(syn2, *batches[0], depth=depth)
+    syn2.counter.fill_(100)
+    t_dec.prime_pipeline(batches[:depth])        # queue = batches 0..depth-1, drawn with counters 101..
+    got = []
+    for i in range(steps):
+        for dst, src in zip(static, batches[i + depth]):
+            dst.copy_(src)                       # records of the batch that refills the freed slot
+        got.append(t_dec.replay().clone())
+    t_dec.join()
+    torch.cuda.synchronize()
+    assert torch.allclose(want[0], got[0], rtol=1e-5, atol=1e-6), (want[0], got[0])
+    for w, g in zip(want, got):
+        assert torch.allclose(w, g, rtol=1e-2, atol=1e-5), (w, g)
+    assert (t_seq.v.flat - t_dec.v.flat).abs().mean().item() < 1e-4
