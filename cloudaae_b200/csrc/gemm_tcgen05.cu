@@ -71,6 +71,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// ... and the same with global += shared (TMA reduction; element type from the tensor map)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -135,7 +140,8 @@ struct GemmParams {
   int atomic;       // split-K: reduce with red.global.add
   int a_mn, b_mn;   // operand majors (0 = K-major, 1 = MN-major)
   uint32_t idesc;
-  int tma_store;    // 128 x 128 kernel: write C with TMA bulk stores from a swizzled staging box (map_c valid)
+  int tma_store;    // 128 x 128 kernel: 1 = write C with TMA bulk stores from a swizzled staging box (map_c valid),
+                    // 2 = C += tile with TMA bulk reductions (accumulate without split-K)
 };
 
 __global__ void __launch_bounds__(TTHREADS)
@@ -260,7 +266,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&map_c, box, n0 + c0, m0 + quad * 32);
+            if (p.tma_store == 2) tma_reduce_add_2d(&map_c, box, n0 + c0, m0 + quad * 32);   // C += tile
+            else tma_store_2d(&map_c, box, n0 + c0, m0 + quad * 32);
             tma_store_commit();
           }
           sbuf ^= 1;
@@ -889,11 +896,11 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
   CUtensorMap map_c = map_a;   // placeholder unless the TMA-store epilogue applies
   static const bool tma_store_enabled = [] { const char* e = getenv("CAAE_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
   p.tma_store = 0;
-  if (tma_store_enabled && !p.atomic && !p.accumulate && N % 32 == 0 && ldc % 4 == 0 && M >= 4096 &&
+  if (tma_store_enabled && !p.atomic && N % 32 == 0 && ldc % 4 == 0 && M >= 4096 &&
       (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
     rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc);
     if (rc) return rc;
-    p.tma_store = 1;
+    p.tma_store = p.accumulate ? 2 : 1;
   }
   gemm_tf32_kernel<<<grid, TTHREADS, TSMEM_BYTES, s>>>(map_a, map_b, map_c, p);
   return CAAE_LAUNCH_STATUS();

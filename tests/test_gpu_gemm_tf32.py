@@ -118,3 +118,9 @@ def test_gemm_tf32_tma_store_epilogue(M, N, K, ldc, tb):
     rows[:3] = torch.tensor([0, 127, M - 1], device="cuda")
     want = A[rows].double() @ Bm.double() + bias.double()
     assert (C[rows, :N].double() - want).abs().max().item() <= 4e-3 * scale / K ** 0.5
+    # accumulate on top: C += A B through TMA bulk reductions (the EdgeConv data gradients into d_hcat slices)
+    _run(0, tb, M, N, K, A, K, B, B.shape[1], C, ldc, None, 1)
+    torch.cuda.synchronize()
+    assert (C[rows, :N].double() - (2 * want - bias.double())).abs().max().item() <= 8e-3 * scale / K ** 0.5
+    assert (C[:M, :N] - (2 * ref - bias)).abs().max().item() <= 8e-3 * scale
+    assert (C[:M, N:] == 7.0).all() and (C[M:] == 7.0).all()
