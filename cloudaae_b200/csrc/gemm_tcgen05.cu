@@ -250,7 +250,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // every MMA has completed (tmem_full), so the operand stages are free: the A stages become the staging
         // boxes (two 32-row x 128-byte SWIZZLE_128B boxes per epilogue warp) of one TMA store per chunk —
         // full 128-byte lines instead of 16 bytes to 32 different lines per STG.128; rows past M are clipped
-        if (n0 + c0 < p.N) {
+        if (n0 + c0 < p.N && m0 + quad * 32 < p.M) {
           const uint32_t box = smem_a + (uint32_t)(warp - 2) * 8192u + (uint32_t)sbuf * 4096u;
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
@@ -346,7 +346,7 @@ constexpr int BIG_THREADS = 320;   // TMA warp, MMA warp, eight epilogue warps
 template <int BN, int MH_, bool A_MN>
 __global__ void __launch_bounds__(BIG_THREADS)
 gemm_tf32_big_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const GemmParams p) {
+                     const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   using Cfg = BigCfg<BN, MH_>;
   constexpr int ST = Cfg::STAGES, MH = Cfg::MH;
   __shared__ __align__(16) float s_bias[BN];
@@ -442,12 +442,39 @@ gemm_tf32_big_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     constexpr int NWORK = MH * NC;                    // (row block, chunk) items; this warp takes item % 2 == part
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
     auto taddr = [&](int w) { return tlane + (uint32_t)((w / NC) * Cfg::ACC_COLS + (w % NC) * 32); };
+    int sbuf = 0;
     auto store_item = [&](uint32_t (&r)[32], int w) {
       if (num_kb <= 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
       const int h = w / NC, c0 = (w % NC) * 32;
+      if (p.tma_store) {
+        // the operand stages are free once tmem_full has fired: their first 64 KB become the staging boxes (two
+        // 32-row x 128-byte SWIZZLE_128B boxes per epilogue warp) of one TMA store / reduction per chunk
+        if (n0 + c0 >= p.N || m0 + h * TBM + quad * 32 >= p.M) return;   // nothing of this box lies inside C
+        const uint32_t box = smem_a + (uint32_t)(warp - 2) * 8192u + (uint32_t)sbuf * 4096u;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const uint32_t rowaddr = box + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          st_shared_v4(rowaddr + (uint32_t)(((j >> 2) ^ (lane & 7)) << 4), v);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.tma_store == 2) tma_reduce_add_2d(&map_c, box, n0 + c0, m0 + h * TBM + quad * 32);
+          else tma_store_2d(&map_c, box, n0 + c0, m0 + h * TBM + quad * 32);
+          tma_store_commit();
+        }
+        sbuf ^= 1;
+        return;
+      }
       const int row = m0 + h * TBM + quad * 32 + lane;
       if (row >= p.M || n0 + c0 >= p.N) return;
       float* crow = p.C + (size_t)row * p.ldc + n0 + c0;
@@ -496,6 +523,7 @@ gemm_tf32_big_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (p.tma_store && lane == 0) tma_store_wait_all();   // the staging boxes must outlive the bulk operations reading them
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -854,12 +882,19 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
     }
     dim3 grid(N / bn, (M + mh * TBM - 1) / (mh * TBM), sp);
     CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
+    CUtensorMap map_c2 = map_a2;   // placeholder unless the TMA epilogue applies
+    static const bool big_tma = [] { const char* e = getenv("CAAE_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+    if (big_tma && N % 32 == 0 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+      rc = make_map_c(&map_c2, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc);
+      if (rc) return rc;
+      p.tma_store = (p.atomic || p.accumulate) ? 2 : 1;   // split-K partial tiles and C += combine by bulk reduction
+    }
 #define CAAE_LAUNCH_BIG(BN_, MH_, AMN_)                                                                              \
     do {                                                                                                             \
       cudaError_t e_ = cudaFuncSetAttribute(gemm_tf32_big_kernel<BN_, MH_, AMN_>,                                    \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BigCfg<BN_, MH_>::SMEM); \
       if (e_ != cudaSuccess) return (int)e_;                                                                         \
-      gemm_tf32_big_kernel<BN_, MH_, AMN_><<<grid, BIG_THREADS, BigCfg<BN_, MH_>::SMEM, s>>>(map_a2, map_b2, p);        \
+      gemm_tf32_big_kernel<BN_, MH_, AMN_><<<grid, BIG_THREADS, BigCfg<BN_, MH_>::SMEM, s>>>(map_a2, map_b2, map_c2, p);        \
     } while (0)
     if (big_wgrad) CAAE_LAUNCH_BIG(128, 3, true);
     else CAAE_LAUNCH_BIG(160, 2, false);

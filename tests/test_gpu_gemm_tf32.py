@@ -124,3 +124,29 @@ def test_gemm_tf32_tma_store_epilogue(M, N, K, ldc, tb):
     assert (C[rows, :N].double() - (2 * want - bias.double())).abs().max().item() <= 8e-3 * scale / K ** 0.5
     assert (C[:M, :N] - (2 * ref - bias)).abs().max().item() <= 8e-3 * scale
     assert (C[:M, N:] == 7.0).all() and (C[M:] == 7.0).all()
+
+
+@pytest.mark.parametrize("ta,tb,M,N,K", [(0, 1, 32768, 320, 1024), (0, 0, 19300, 320, 520), (1, 0, 320, 1024, 32768),
+                                         (1, 0, 300, 512, 20000)])
+def test_gemm_tf32_big_tile_tma_epilogue(ta, tb, M, N, K):
+    """The large-tile kernels with an aligned row pitch: 256 x 160 tiles (dgcnn_agg data gradient) store through
+    TMA, the 3 x 128-row split-K weight gradient combines its partial tiles with TMA bulk reductions."""
+    g = torch.Generator("cuda").manual_seed(5 + M + K)
+    A = torch.randn((K, M) if ta else (M, K), device="cuda", generator=g)
+    B = torch.randn((N, K) if tb else (K, N), device="cuda", generator=g) * 0.05
+    C = torch.full((M + 2, N), 7.0, device="cuda")
+    _run(ta, tb, M, N, K, A, A.shape[1], B, B.shape[1], C, N)
+    torch.cuda.synchronize()
+    Am, Bm = (A.T if ta else A), (B.T if tb else B)
+    ref = Am @ Bm
+    scale = (Am[:256].abs().double() @ Bm.abs().double()).max().item()
+    assert (C[:M] - ref).abs().max().item() <= 4e-3 * scale
+    assert (C[M:] == 7.0).all()
+    rows = torch.randint(0, M, (64,), device="cuda", generator=g)
+    rows[:2] = torch.tensor([0, M - 1], device="cuda")
+    want = Am[rows].double() @ Bm.double()
+    assert (C[rows].double() - want).abs().max().item() <= 4e-3 * scale / K ** 0.5
+    _run(ta, tb, M, N, K, A, A.shape[1], B, B.shape[1], C, N, None, 1)   # C += A B
+    torch.cuda.synchronize()
+    assert (C[rows].double() - 2 * want).abs().max().item() <= 8e-3 * scale / K ** 0.5
+    assert (C[M:] == 7.0).all()
