@@ -11,7 +11,8 @@
 //
 // Design: one CTA per segment, the WHOLE refinement (all rounds, all iterations) in one launch: the
 // transformed model (fp64) and the segment live in shared memory, each thread searches the nearest
-// target for its source points by brute force (256 targets: a KD-tree would only add divergence),
+// target for its source points by brute force (256 targets: a KD-tree would only add divergence; an fp32 scan with a
+// rigorous error margin picks the winner, float64 confirms it — the float64 pipe was the bound, ncu: 60 % active),
 // the 17 Kabsch sums are reduced in a fixed order, and one thread solves the rotation with Horn's
 // quaternion form (largest eigenvector of a symmetric 4x4, cyclic Jacobi in fp64) — the same optimum
 // as Umeyama's SVD with its reflection guard whenever that optimum is unique.
@@ -115,6 +116,8 @@ icp_refine_kernel(int ns, int src_stride, const float* __restrict__ source, cons
   extern __shared__ __align__(16) double s_dyn[];
   double* s_pcd = s_dyn;           // [ns][3] current transformed source
   double* s_tgt = s_dyn + ns * 3;  // [nt][3]
+  // [nt] fp32 copy relative to c0 (nearest-target prefilter), 16-byte aligned whatever the parity of ns + nt
+  float4* s_tgf = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(s_tgt + nt * 3) + 15) & ~(uintptr_t)15);
   __shared__ double s_red[kIcpWarps][kIcpSums];
   __shared__ double s_sum[kIcpSums];
   __shared__ double s_T[12];   // accumulated transformation, rows of [R | t]
@@ -130,6 +133,10 @@ icp_refine_kernel(int ns, int src_stride, const float* __restrict__ source, cons
   if (t < 12) s_T[t] = T_init[(size_t)seg * 16 + t];
   __syncthreads();
   const double c0[3] = {nt > 0 ? s_tgt[0] : 0.0, nt > 0 ? s_tgt[1] : 0.0, nt > 0 ? s_tgt[2] : 0.0};
+  for (int j = t; j < nt; j += kIcpThreads)
+    s_tgf[j] = make_float4((float)(s_tgt[j * 3 + 0] - c0[0]), (float)(s_tgt[j * 3 + 1] - c0[1]),
+                           (float)(s_tgt[j * 3 + 2] - c0[2]), 0.f);
+  __syncthreads();
 
   double fit = 0.0, rmse = 0.0;
   int total_iters = 0;
@@ -144,10 +151,32 @@ icp_refine_kernel(int ns, int src_stride, const float* __restrict__ source, cons
       const double x = s_pcd[i * 3 + 0], y = s_pcd[i * 3 + 1], z = s_pcd[i * 3 + 2];
       double best = r2;
       int bj = -1;
+      // fp32 prefilter: the two smallest squared distances over the targets.  When they are further apart than
+      // the fp32 evaluation can be wrong, the fp32 winner IS the float64 nearest target and one exact evaluation
+      // settles the radius test; otherwise (near-ties, duplicates) the exact float64 scan below decides.
+      const float xf = (float)(x - c0[0]), yf = (float)(y - c0[1]), zf = (float)(z - c0[2]);
+      float m1 = 3.0e38f, m2 = 3.0e38f;
+      int j1 = -1;
       for (int j = 0; j < nt; ++j) {
-        const double dx = x - s_tgt[j * 3 + 0], dy = y - s_tgt[j * 3 + 1], dz = z - s_tgt[j * 3 + 2];
+        const float4 tg = s_tgf[j];
+        const float ex = tg.x - xf, ey = tg.y - yf, ez = tg.z - zf;
+        const float d = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+        if (d < m1) { m2 = m1; m1 = d; j1 = j; } else m2 = fminf(m2, d);
+      }
+      // error of d: coordinates relative to c0 rounded to fp32 (|coordinate| < 8 m: 5e-7 each) and the fp32 arithmetic
+      const float kDelta = 5e-7f;
+      const float err = 4.f * kDelta * sqrtf(3.f * m1) + 12.f * kDelta * kDelta + 4e-7f * m1;
+      const float err2 = 4.f * kDelta * sqrtf(3.f * m2) + 12.f * kDelta * kDelta + 4e-7f * m2;
+      if (j1 >= 0 && m2 - m1 > err + err2) {
+        const double dx = x - s_tgt[j1 * 3 + 0], dy = y - s_tgt[j1 * 3 + 1], dz = z - s_tgt[j1 * 3 + 2];
         const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        if (d < best) { best = d; bj = j; }  // strict <: first nearest, and strictly inside the radius
+        if (d < r2) { best = d; bj = j1; }
+      } else {
+        for (int j = 0; j < nt; ++j) {
+          const double dx = x - s_tgt[j * 3 + 0], dy = y - s_tgt[j * 3 + 1], dz = z - s_tgt[j * 3 + 2];
+          const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          if (d < best) { best = d; bj = j; }  // strict <: first nearest, and strictly inside the radius
+        }
       }
       if (bj >= 0) {
         const double xr = x - c0[0], yr = y - c0[1], zr = z - c0[2];
@@ -249,7 +278,7 @@ extern "C" int caae_icp_refine(int b, int ns, int src_stride, const float* sourc
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(T_init == nullptr || T_out == nullptr, CAAE_E_NULLPTR);
   CAAE_RETURN_IF((ns > 0 && source == nullptr) || (nt > 0 && target == nullptr), CAAE_E_NULLPTR);
-  const size_t smem = ((size_t)ns + (size_t)nt) * 3 * sizeof(double);
+  const size_t smem = ((size_t)ns + (size_t)nt) * 3 * sizeof(double) + (size_t)nt * sizeof(float4) + 16;
   CAAE_RETURN_IF(smem > 200 * 1024, CAAE_E_UNSUPPORTED);
   cudaError_t e = cudaFuncSetAttribute(icp_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

@@ -74,6 +74,39 @@ class CloudAAEInference:
         return out
 
 
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, with_target: bool = True, with_pose_labels: bool = True, seg_points: int | None = None):
+        """Capture `forward` on static input buffers (the ~50 launches of a batch become one graph launch:
+        eval-mode batches are launch-bound otherwise).  Returns the static inputs dict {'segment', 'class_id',
+        'target', 'translation', 'axisangle'} (absent labels are None); fill them, then `replay()` returns the
+        same output dict as `forward` (views of reused buffers)."""
+        B, N = self.B, self.N
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        st = {"segment": torch.zeros(B, seg_points or N, 3, **f32),
+              "class_id": torch.zeros(B, dtype=torch.int32, device=self.dev),
+              "target": torch.zeros(B, N, 3, **f32) if with_target else None,
+              "translation": torch.zeros(B, 3, **f32) if with_pose_labels else None,
+              "axisangle": torch.zeros(B, 3, **f32) if with_pose_labels else None}
+        args = (st["segment"], st["class_id"], st["target"], st["translation"], st["axisangle"])
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.forward(*args)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        before = _capi.COUNTER[0]
+        with torch.cuda.graph(self._graph, stream=side):
+            self._graph_out = self.forward(*args)
+        self.launches_per_batch = _capi.COUNTER[0] - before
+        self.static = st
+        return st
+
+    def replay(self):
+        self._graph.replay()
+        return self._graph_out
+
+
 def run_sharded(infer: CloudAAEInference, segments, class_ids, targets, translations, axisangles, rank: int = 0,
                 world: int = 1):
     """Process this rank's contiguous shard of a segment list (device tensors, leading dim = total).
