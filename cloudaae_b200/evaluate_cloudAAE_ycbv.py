@@ -41,15 +41,17 @@ class SegmentFrontEnd:
 
     def __init__(self, depth: torch.Tensor, label: torch.Tensor, intrinsics: torch.Tensor,
                  threshold_distance_per_class: torch.Tensor, cap: int = 32768):
-        for t, name in ((depth, "depth"), (label, "label"), (intrinsics, "intrinsics"),
-                        (threshold_distance_per_class, "threshold_distance_per_class")):
-            _capi.require_cuda(t, f"SegmentFrontEnd({name})")
         if depth.dim() != 3 or label.shape != depth.shape:
             raise InvalidArgumentError("SegmentFrontEnd expects depth and label of shape (frames, height, width)")
         if depth.dtype not in (torch.uint16, torch.int16) or label.dtype != torch.uint8:
             raise InvalidArgumentError("SegmentFrontEnd expects 16-bit depth and uint8 label")
         if intrinsics.shape != (depth.shape[0], 5) or intrinsics.dtype != torch.float32:
             raise InvalidArgumentError("SegmentFrontEnd expects float32 intrinsics of shape (frames, 5)")
+        if threshold_distance_per_class.dim() != 1:
+            raise InvalidArgumentError("SegmentFrontEnd expects one distance threshold per class")
+        for t, name in ((depth, "depth"), (label, "label"), (intrinsics, "intrinsics"),
+                        (threshold_distance_per_class, "threshold_distance_per_class")):
+            _capi.require_cuda(t, f"SegmentFrontEnd({name})")
         self.depth, self.label = depth.contiguous(), label.contiguous()
         self.intr = intrinsics.contiguous()
         self.thr = threshold_distance_per_class.to(torch.float32).contiguous()
@@ -118,9 +120,11 @@ class SegmentFrontEnd:
 
 
 def _radius_outliers(xyz, n_pts, nb_points, radius, min_keep):
-    _capi.require_cuda(xyz, "get_outlier_idx")
     if xyz.dim() != 3 or xyz.shape[2] != 3 or xyz.dtype != torch.float32:
         raise InvalidArgumentError("get_outlier_idx expects float32 xyz of shape (segments, cap, 3)")
+    if nb_points < 0 or not radius >= 0:
+        raise InvalidArgumentError("get_outlier_idx expects nb_points >= 0 and radius >= 0")
+    _capi.require_cuda(xyz, "get_outlier_idx")
     xyz = xyz.contiguous()
     S, cap, _ = xyz.shape
     n_pts = _as_i32(n_pts, xyz.device)
@@ -160,13 +164,12 @@ def _fps_seeded(xyz, n_pts, first_idx, k):
 # ---- single-segment functions under the reference's names ---------------------------------------------
 
 def get_pointcloud(depth: torch.Tensor, fx, fy, cx, cy, depth_scaling_factor) -> torch.Tensor:
-    """depth u16 [h,w] -> f32 [h*w,3] (evaluate…:164-178).  Implemented as a segment whose mask is every
-    pixel with non-zero depth is NOT what the reference does — it returns all pixels — so this runs the
-    same arithmetic kernel with an all-ones label and re-inserts (0,0,0) rows for zero-depth pixels, which
-    is exactly what the formula yields for depth 0."""
-    _capi.require_cuda(depth, "get_pointcloud")
+    """depth u16 [h,w] -> f32 [h*w,3] for ALL pixels (evaluate…:164-178).  Runs the segment kernel with an
+    all-ones label (its mask drops zero-depth pixels) and scatters the rows back by pixel id; a zero-depth pixel
+    keeps the row (0, 0, 0), which is what the formula yields for depth 0."""
     if depth.dim() != 2:
         raise InvalidArgumentError("get_pointcloud expects a (height, width) depth image")
+    _capi.require_cuda(depth, "get_pointcloud")
     h, w = depth.shape
     dev = depth.device
     label = torch.ones(1, h, w, dtype=torch.uint8, device=dev)
@@ -190,10 +193,14 @@ def FPS_random(pts: torch.Tensor, K: int, seq_id=None, frame_id=None, class_id=N
                rng: _random.Random | None = None) -> torch.Tensor:
     """One segment (n,>=3) -> int64 [K] (evaluate…:230-247).  seq_id/frame_id/class_id only feed the
     reference's log lines; `first_idx` (or `rng`) replaces the module-level random.randint."""
-    _capi.require_cuda(pts, "FPS_random")
+    if pts.dim() != 2 or pts.shape[1] < 3:
+        raise InvalidArgumentError("FPS_random expects pts of shape (points, >=3)")
     n = pts.shape[0]
     if n == 0:
         raise ValueError("FPS_random: empty segment (random.randint(0, -1) raises in the reference)")
+    if K <= 0:
+        raise InvalidArgumentError("FPS_random expects a positive K")
+    _capi.require_cuda(pts, "FPS_random")
     if first_idx is None:
         first_idx = (rng or _random).randint(0, n - 1)
     xyz = pts[:, 0:3].to(torch.float32).reshape(1, n, 3).contiguous()
@@ -228,8 +235,6 @@ def icp_refine(source: torch.Tensor, target: torch.Tensor, init: torch.Tensor, s
     object models [21,2048,6]; `source_of_seg` i32[B] picks the model of each segment, default = segment
     index), target f32[B,nt,3], init f64[B,4,4].  Returns (T f64[B,4,4], fitness f64[B], inlier_rmse f64[B],
     iterations i32[B])."""
-    for t, name in ((source, "source"), (target, "target"), (init, "init")):
-        _capi.require_cuda(t, f"icp_refine({name})")
     if source.dim() != 3 or source.shape[2] < 3 or source.dtype != torch.float32:
         raise InvalidArgumentError("icp_refine expects float32 source of shape (models, points, >=3)")
     if target.dim() != 3 or target.shape[2] != 3 or target.dtype != torch.float32:
@@ -239,6 +244,8 @@ def icp_refine(source: torch.Tensor, target: torch.Tensor, init: torch.Tensor, s
         raise InvalidArgumentError("icp_refine expects float64 init of shape (batch, 4, 4)")
     if source_of_seg is None and source.shape[0] != B:
         raise InvalidArgumentError("icp_refine: without source_of_seg the source batch must equal the target batch")
+    for t, name in ((source, "source"), (target, "target"), (init, "init")):
+        _capi.require_cuda(t, f"icp_refine({name})")
     source, target, init = source.contiguous(), target.contiguous(), init.contiguous()
     sel = None if source_of_seg is None else _as_i32(source_of_seg, target.device)
     dev = target.device

@@ -56,3 +56,31 @@ def fps_ties_inputs() -> np.ndarray:
 
 def random_clouds(seed: int, b: int, n: int, scale: float = 0.1) -> np.ndarray:
     return (np.random.default_rng(seed).standard_normal((b, n, 3)) * scale).astype(np.float32)
+
+
+# ---- evaluation front end / ICP (oracle/evaluation.py, tests/golden/eval_golden.npz) ---------------------
+EVAL_GOLDEN_CLASSES = (0, 3, 7)
+
+
+def eval_golden_frame():
+    """One synthetic 480 x 640 frame: YCB models 0, 3, 7 posed by record 0 of their class (depth u16, label u8)."""
+    from cloudaae_b200.data.synthetic_frames import render_frame
+    clouds = posed_ycb_clouds(0)
+    return render_frame(clouds[list(EVAL_GOLDEN_CLASSES)], list(EVAL_GOLDEN_CLASSES), splat=1, seed=0)
+
+
+def eval_golden_icp_case(cls: int = 9, seed: int = 55):
+    """A 256-point segment cut from the camera-facing half of a posed model + a perturbed initial pose."""
+    from scipy.spatial.transform import Rotation
+    models = ycb_models()
+    t, a, c = ycb_poses()
+    rec = cls * (len(c) // 21) + 3
+    rng = np.random.default_rng(seed)
+    R = Rotation.from_rotvec(a[rec].astype(np.float64)).as_matrix()
+    posed = models[cls].astype(np.float64) @ R.T + t[rec]
+    vis = posed[posed[:, 2] < np.median(posed[:, 2])]
+    target = (vis[rng.permutation(len(vis))[:256]] + rng.normal(0, 5e-4, (256, 3))).astype(np.float32)
+    init = np.eye(4)
+    init[:3, :3] = Rotation.from_rotvec(rng.normal(0, 0.03, 3)).as_matrix() @ R
+    init[:3, 3] = t[rec] + rng.normal(0, 0.003, 3)
+    return models[cls], target, init

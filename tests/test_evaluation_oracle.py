@@ -96,3 +96,23 @@ def test_icp_refine_pulls_a_perturbed_pose_back():
         after = np.abs(models[cls] @ T[:3, :3].T + T[:3, 3] - posed).max()
         assert after < 0.2 * before and fit > 0.05 and rmse < 0.005 and iters >= 10
         np.testing.assert_allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-12)
+
+
+def test_oracle_reproduces_the_committed_golden_vectors():
+    """tests/golden/eval_golden.npz (written by tests/golden/make_golden_eval.py) pins the oracle itself: a change
+    of NumPy / SciPy or of the restatement that moves any of these outputs must be noticed."""
+    import os
+    g = np.load(os.path.join(cases.GOLDEN, "eval_golden.npz"))
+    depth, label = cases.eval_golden_frame()
+    assert (g["frame_checksum"] == [int(depth.astype(np.int64).sum()), int(label.astype(np.int64).sum())]).all()
+    for c in cases.EVAL_GOLDEN_CLASSES:
+        org, flt, pix, mean = E.segment_extract(depth, label, E.YCBV_INTRINSICS, c, 0.2)
+        idx = E.get_outlier_idx(flt)
+        assert (g[f"seg{c}_counts"] == [len(org), len(flt), len(idx), E.num_valid_points(idx)]).all()
+        assert (g[f"seg{c}_mean"] == mean).all()
+        assert (g[f"seg{c}_pix_head"] == pix[:64]).all() and (g[f"seg{c}_inlier_head"] == idx[:64]).all()
+        assert (g[f"seg{c}_fps"] == E.FPS_random(flt, 64, 5)).all()
+    model, target, init = cases.eval_golden_icp_case()
+    T, fit, rmse, it = E.icp_refine(model, target, init)
+    np.testing.assert_allclose(T, g["icp_T"], atol=1e-9)
+    np.testing.assert_allclose([fit, rmse, it], g["icp_stats"], atol=1e-9)

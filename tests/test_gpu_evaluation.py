@@ -212,3 +212,30 @@ def test_pose_to_matrix_is_rodrigues():
     for i in range(4):
         np.testing.assert_allclose(T[i, :3, :3], Rotation.from_rotvec(a[i].astype(np.float64)).as_matrix(), atol=1e-12)
         np.testing.assert_allclose(T[i, :3, 3], t[i].astype(np.float64))
+
+
+def test_front_end_and_icp_against_committed_golden_vectors():
+    """The same golden file the CPU suite pins the oracle with (tests/golden/eval_golden.npz)."""
+    import os
+    g = np.load(os.path.join(cases.GOLDEN, "eval_golden.npz"))
+    depth, label = cases.eval_golden_frame()
+    classes = list(cases.EVAL_GOLDEN_CLASSES)
+    fe = EV.SegmentFrontEnd(cu(depth[None]), cu(label[None]), cu(E.YCBV_INTRINSICS[None]),
+                            cu(np.full(21, 0.2, np.float32)), cap=20000)
+    e = fe.extract([0] * len(classes), classes)
+    idx, n_in = EV._radius_outliers(e["xyz_org_distance_filtered"], e["num_point_after_filter"], 100, 0.02, 512)
+    first = cu(np.full(len(classes), 5, np.int32))
+    fps, _ = EV._fps_seeded(e["xyz_org_distance_filtered"], e["num_point_after_filter"], first, 64)
+    for s, c in enumerate(classes):
+        n_flt, n_inl = int(e["num_point_after_filter"][s]), int(n_in[s])
+        num_valid = n_inl - int(idx[s, 0] == 0)
+        assert (g[f"seg{c}_counts"] == [int(e["n_org"][s]), n_flt, n_inl, num_valid]).all()
+        assert (g[f"seg{c}_mean"] == np_(e["mean"][s])).all()
+        assert (g[f"seg{c}_pix_head"] == np_(e["pix"][s, :64])).all()
+        assert (g[f"seg{c}_inlier_head"] == np_(idx[s, :64])).all()
+        assert (g[f"seg{c}_fps"] == np_(fps[s])).all()
+    model, target, init = cases.eval_golden_icp_case()
+    T, fit, rmse, it = EV.icp_refine(cu(model[None]), cu(target[None]), cu(init[None]))
+    np.testing.assert_allclose(np_(T)[0], g["icp_T"], atol=1e-6)
+    assert abs(float(fit[0]) - g["icp_stats"][0]) < 1e-3 and abs(float(rmse[0]) - g["icp_stats"][1]) < 1e-6
+    assert abs(int(it[0]) - int(g["icp_stats"][2])) <= 2

@@ -57,3 +57,37 @@ def test_no_cpu_kernels():
         tf_sampling.farthest_point_sample(4, a)
     with pytest.raises(NotImplementedError, match="no CPU kernel"):
         tf_sampling.gather_point(a, torch.zeros(2, 4, dtype=torch.int32))
+
+
+def test_evaluation_front_end_and_icp_argument_errors():
+    """cloudaae_b200/evaluate_cloudAAE_ycbv.py: shape / dtype violations first, then 'no CPU kernel'."""
+    from cloudaae_b200 import evaluate_cloudAAE_ycbv as EV
+    for name in ("get_pointcloud", "get_outlier_idx", "FPS_random", "icp_refine", "SegmentFrontEnd", "pose_to_matrix"):
+        assert hasattr(EV, name)
+    depth = torch.zeros(2, 4, 6, dtype=torch.int16)
+    label = torch.zeros(2, 4, 6, dtype=torch.uint8)
+    intr = torch.ones(2, 5)
+    thr = torch.full((21,), 0.2)
+    with pytest.raises(InvalidArgumentError, match="frames, height, width"):
+        EV.SegmentFrontEnd(depth[0], label[0], intr, thr)
+    with pytest.raises(InvalidArgumentError, match="16-bit depth"):
+        EV.SegmentFrontEnd(depth.float(), label, intr, thr)
+    with pytest.raises(InvalidArgumentError, match=r"\(frames, 5\)"):
+        EV.SegmentFrontEnd(depth, label, intr[:, :4], thr)
+    with pytest.raises(NotImplementedError, match="CUDA"):
+        EV.SegmentFrontEnd(depth, label, intr, thr)
+    with pytest.raises(InvalidArgumentError, match="height, width"):
+        EV.get_pointcloud(depth, 1.0, 1.0, 0.0, 0.0, 1.0)
+    with pytest.raises(NotImplementedError):
+        EV.get_outlier_idx(torch.zeros(10, 3), 100, 0.02, 0.5)
+    with pytest.raises(ValueError, match="empty segment"):
+        EV.FPS_random(torch.zeros(0, 3), 4)
+    with pytest.raises(NotImplementedError):
+        EV.FPS_random(torch.zeros(5, 3), 4, first_idx=0)
+    src, tgt, init = torch.zeros(2, 16, 3), torch.zeros(2, 8, 3), torch.zeros(2, 4, 4, dtype=torch.float64)
+    with pytest.raises(InvalidArgumentError, match="float64 init"):
+        EV.icp_refine(src, tgt, init.float())
+    with pytest.raises(InvalidArgumentError, match="source_of_seg"):
+        EV.icp_refine(src[:1], tgt, init)
+    with pytest.raises(NotImplementedError):
+        EV.icp_refine(src, tgt, init)
