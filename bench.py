@@ -658,6 +658,69 @@ def run_reference_train(args):
     }
 
 
+def run_reference_infer(args):
+    """--impl reference --workload infer: the evaluation graph (evaluate_cloudAAE_ycbv.py:437-474) on this box's
+    host cores — torch-CPU fp32 restatement of the TF graph with moving-average batch norm, FPS 1024 -> 256 by the
+    oracle's C restatement of the reference CUDA kernel (the reference has no CPU FPS op), chamfer through the
+    reference's own CPU OpKernel when oracle/_ref is built.  Segments are synthesized before the timed region.
+    Each step is a bounded SAMPLE (64 segments) of the 4096-segment list."""
+    import multiprocessing as mp
+
+    import torch
+
+    from oracle import model_ref as MR
+    from oracle import ops as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = 64
+    models = np.load(os.path.join(ROOT, "tests", "golden", "ycb_models_xyz.npy"))
+    params, _, _, _ = _ref_train_setup(b)
+    for k in params:
+        if k.endswith("ema_var"):
+            params[k].fill_(1.0)
+    use_ref = O.have_ref()
+    bt = pose_batches(b, seed=0, pool=1)[0]
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_synth_one, [(models[bt["class_id"][k]], bt["axisangle"][k], bt["translation"][k], k) for k in range(b)])
+    vis = torch.from_numpy(np.stack([r[0] for r in res])); tgt = np.stack([r[1][:TRAIN_N] for r in res])
+    cls = torch.from_numpy(bt["class_id"])
+
+    def step():
+        with torch.no_grad():
+            x, mean = MR.prepare_input(vis, cls, torch.zeros(b, TRAIN_N, 3), num_point=TRAIN_N)
+            recon, rot, trans_res, _ = MR.get_model_dgcnn_mean_6d(x, params, False, False, 10, None)
+            recon = (recon + mean.unsqueeze(1)).numpy()
+            idx = O.fps(recon, TRAIN_N, threads=cores)
+            sub = O.gather(recon, idx)
+            fn = O.ref_cpu_nn_distance if use_ref else (lambda a, c: O.nn_distance(a, c, "cpu", threads=cores))
+            d1, _, d2, _ = fn(sub, tgt)
+            MR.get_translation_error(trans_res + mean, torch.from_numpy(bt["translation"]))
+            MR.get_rotation_error(rot.double(), torch.from_numpy(bt["axisangle"]).double())
+        return float((d1 + d2).mean())
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = b * args.steps / dt
+    sample = (f"{args.steps} steps x {b}-segment sample of the {INFER_TOTAL}-segment list: torch-CPU fp32 restatement of the "
+              f"TF graph (moving-average BN) on {cores} threads, FPS by the oracle's C restatement, chamfer via "
+              f"{'the reference CPU OpKernel (oracle/_ref)' if use_ref else 'the oracle port'}")
+    return {
+        "impl": "reference", "metric": "inference segments/sec", "value": value, "unit": "segments/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same fixtures as the GPU arm)",
+        "config": {"workload": "batched inference over all 21 YCB classes, BASELINE.json configs[4]",
+                   "segments": INFER_TOTAL, "reference_sample_per_step": b, "num_point": TRAIN_N},
+        "cpu_baseline": {"value": value, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
 def cpu_baseline_train(seconds: float = 12.0):
     """cpu_baseline leg of the default run: the same reference step, run for ~`seconds` s on rank 0."""
     class A:  # minimal args
@@ -820,7 +883,12 @@ def run_ours_infer(args, rank, world, local_rank):
     _, fit, rmse, iters = EV.icp_refine(src6, seg[0], T0, source_of_seg=cls[0])
     ms = total_ms / args.steps
     n_seg = nb * B * world
+
+    class RefArgs:
+        gpus, warmup, steps = 1, 1, 3
+    cpu_ref = run_reference_infer(RefArgs)["cpu_baseline"]
     return {
+        "cpu_baseline": cpu_ref,
         "metric": "inference segments/sec", "value": n_seg / (ms * 1e-3), "unit": "segments/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 (dgcnn_agg contraction: tf32 multiply, f32 accumulate)",
@@ -857,7 +925,8 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            fn = run_reference_train if args.workload in ("auto", "train") else run_reference_ops
+            fn = {"auto": run_reference_train, "train": run_reference_train,
+                  "infer": run_reference_infer}.get(args.workload, run_reference_ops)
             print(json.dumps(fn(args)), flush=True)
         return 0
 
