@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcloudaae_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2   # 2: evaluation front end + ICP entry points
 
 _int = ctypes.c_int
 _ptr = ctypes.c_void_p
@@ -79,7 +79,7 @@ _SIGNATURES = {
     "caae_segment_extract": "iiiippppppipppppp" "p",
     "caae_radius_outlier": "iippidippp" "p",
     "caae_fps_seeded_f64": "iiipppppp" "p",
-    "caae_icp_refine": "iiippippddiiddpppp".replace(" ", "") + "p",
+    "caae_icp_refine": "iiippippddiiddpppp" "p",
 }
 _SIGNATURES = {k: [_CODES[c] for c in v] for k, v in _SIGNATURES.items()}
 _SPECIAL = {

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CAAE_ABI_VERSION 1
+#define CAAE_ABI_VERSION 2
 
 /* argument errors (negative); positive return values are cudaError_t */
 #define CAAE_OK 0
