@@ -43,6 +43,7 @@ _SIGNATURES = {
     # model building blocks
     "caae_gemm_f32": "iiiiipipipipi" "p",
     "caae_gemm_tf32": "iiiiipipipipi" "p",
+    "caae_gemm_tf32_stats": "iiipipipipp" "p",
     "caae_knn": "iiiipip" "p",
     "caae_edge_stats": "iiiipipp" "p",
     "caae_edge_apply": "iiiipippppi" "p",
@@ -89,6 +90,7 @@ _SPECIAL = {
     "caae_fps_scratch_bytes": ([_int, _int], ctypes.c_size_t),
     "caae_edge_parts": ([_int, _int, _int, _int, _int], _int),
     "caae_col_parts": ([_int], _int),
+    "caae_gemm_tf32_stats_parts": ([_int, _int, _int, _int], _int),
     "caae_debug_hpr_timing": ([_ptr], _int),
     "caae_gemm_tf32_supported": ([_int, _int, _int, _int, _int, _ptr, _int, _ptr, _int], _int),
 }

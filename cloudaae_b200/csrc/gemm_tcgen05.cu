@@ -140,6 +140,7 @@ struct GemmParams {
   int atomic;       // split-K: reduce with red.global.add
   int a_mn, b_mn;   // operand majors (0 = K-major, 1 = MN-major)
   uint32_t idesc;
+  double* stats_parts;  // persistent kernel: per (row tile, lane quadrant) column sums / sums of squares of C (or NULL)
   int tma_store;    // 128 x 128 kernel: 1 = write C with TMA bulk stores from a swizzled staging box (map_c valid),
                     // 2 = C += tile with TMA bulk reductions (accumulate without split-K)
 };
@@ -653,6 +654,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
       auto taddr = [&](int w) { return tlane + (uint32_t)((w / NC) * TBN + (w % NC) * 32); };
+      double st_sum[2] = {0.0, 0.0}, st_sq[2] = {0.0, 0.0};   // this warp's two column chunks (part, part + 2), both row blocks
       auto store_item = [&](uint32_t (&r)[32], int w) {
         const int h = w / NC, c0 = (w % NC) * 32;
         if (!p.accumulate) {
@@ -676,6 +678,22 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           if (lane == 0) {
             tma_store_2d(&map_c, box, n0 + c0, m0 + h * TBM + quad * 32);
             tma_store_commit();
+          }
+          if (p.stats_parts != nullptr) {
+            // batch-norm statistics of the tile while it sits in shared memory: lane l sums column l of the box
+            // (swizzled address: 32 distinct banks per row), fp32 over the 32 rows, fp64 across boxes
+            const int rmax = min(32, p.M - (m0 + h * TBM + quad * 32));
+            float fs = 0.f, fq = 0.f;
+            const uint32_t col = box + (uint32_t)((lane & 3) << 2);
+            for (int rr = 0; rr < rmax; ++rr) {
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(col + (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7))) << 4)));
+              fs += v;
+              fq = fmaf(v, v, fq);
+            }
+            const int slot = ((w - part) >> 1) & 1;
+            st_sum[slot] += (double)fs;
+            st_sq[slot] += (double)fq;
           }
           sbuf ^= 1;
           return;
@@ -710,6 +728,16 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (p.stats_parts != nullptr && !p.accumulate) {
+        // one partial row per (row tile, lane quadrant): the layout caae_bn_finalize reduces ([row][2][N])
+        double* prow = p.stats_parts + (size_t)((id / tiles_n) * 4 + quad) * 2 * p.N;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int colg = n0 + (part + 2 * sl) * 32 + lane;
+          prow[colg] = st_sum[sl];
+          prow[p.N + colg] = st_sq[sl];
+        }
+      }
     }
     if (lane == 0) tma_store_wait_all();   // the staging boxes must outlive the bulk stores that read them
   }
@@ -789,8 +817,9 @@ extern "C" int caae_gemm_tf32_supported(int transa, int transb, int M, int N, in
   return 1;
 }
 
-extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
-                              int ldb, float* C, int ldc, const float* bias, int accumulate, caae_stream_t stream) {
+static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
+                          int ldb, float* C, int ldc, const float* bias, int accumulate, double* stats_parts,
+                          caae_stream_t stream) {
   CAAE_RETURN_IF(M < 0 || N < 0 || K < 0, CAAE_E_BADSHAPE);
   if (M == 0 || N == 0) return CAAE_OK;
   CAAE_RETURN_IF(!C || !A || !B, CAAE_E_NULLPTR);
@@ -811,6 +840,7 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
 
   GemmParams p;
   p.tma_store = 0;
+  p.stats_parts = nullptr;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
   p.a_mn = transa ? 1 : 0;
   p.b_mn = transb ? 0 : 1;
@@ -822,9 +852,13 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
   const int num_kb = (K + TBK - 1) / TBK;
   // tall / wide / short-K forward contractions: persistent 256 x 128 tiles with the epilogue overlapped
   static const bool persist_enabled = [] { const char* e = getenv("CAAE_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
-  if (persist_enabled && !transa && N % TBN == 0 && N <= PS_MAXN && N >= 512 && M >= 256 * kNumSMs / 2 && num_kb >= 2 &&
-      num_kb <= 16 && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
-      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 3) == 0)) {
+  const bool persist_ok = persist_enabled && !transa && N % TBN == 0 && N <= PS_MAXN && N >= 512 &&
+                          M >= 256 * kNumSMs / 2 && num_kb >= 2 && num_kb <= 16 && ldc % 4 == 0 &&
+                          (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                          (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 3) == 0);
+  if (stats_parts != nullptr && (!persist_ok || accumulate)) return CAAE_E_UNSUPPORTED;
+  p.stats_parts = stats_parts;
+  if (persist_ok) {
     CUtensorMap map_a2, map_b2;
     rc = make_map(&map_a2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
     if (rc) return rc;
@@ -939,4 +973,25 @@ extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const
   }
   gemm_tf32_kernel<<<grid, TTHREADS, TSMEM_BYTES, s>>>(map_a, map_b, map_c, p);
   return CAAE_LAUNCH_STATUS();
+}
+
+extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
+                              int ldb, float* C, int ldc, const float* bias, int accumulate, caae_stream_t stream) {
+  return gemm_tf32_impl(transa, transb, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, nullptr, stream);
+}
+
+// Partial rows caae_gemm_tf32_stats writes for this shape (0: the fused-statistics path does not apply).
+extern "C" int caae_gemm_tf32_stats_parts(int M, int N, int K, int ldc) {
+  static const bool persist_enabled = [] { const char* e = getenv("CAAE_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
+  const int num_kb = (K + TBK - 1) / TBK;
+  if (!persist_enabled || M <= 0 || N % TBN != 0 || N > PS_MAXN || N < 512 || M < 256 * kNumSMs / 2 || num_kb < 2 ||
+      num_kb > 16 || ldc % 4 != 0)
+    return 0;
+  return 4 * ((M + 2 * TBM - 1) / (2 * TBM));
+}
+
+extern "C" int caae_gemm_tf32_stats(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                                    int ldc, const float* bias, double* parts, caae_stream_t stream) {
+  CAAE_RETURN_IF(parts == nullptr, CAAE_E_NULLPTR);
+  return gemm_tf32_impl(0, 0, M, N, K, A, lda, B, ldb, C, ldc, bias, 0, parts, stream);
 }

@@ -778,7 +778,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
     if (r < nv) src = ids[r];
     else if (nv > 0) {  // np.random.choice(visibleId, ...) padding (:38-40)
       const float uu = pad_uniform ? pad_uniform[(size_t)cloud * take + r] : ((float)((r - nv) % nv) + 0.5f) / (float)nv;
-      src = ids[min((int)(uu * (float)nv), nv - 1)];
+      src = ids[max(0, min((int)(uu * (float)nv), nv - 1))];   // clamped: a draw outside [0,1) must not index out of range
     } else src = -1;
     dst[r * 3 + 0] = src >= 0 ? op[src * 3 + 0] : 0.f;
     dst[r * 3 + 1] = src >= 0 ? op[src * 3 + 1] : 0.f;

@@ -223,6 +223,7 @@ class _Engine:
         # the EdgeConv projection next to the kNN search of the same layer.  Every launch of those chains
         # is far too small to fill 148 SMs on its own.  CLOUDAAE_STREAMS=0 serialises everything.
         self.concurrent = os.environ.get("CLOUDAAE_STREAMS", "1") != "0" and self.dev.type == "cuda"
+        self.fused_stats = os.environ.get("CLOUDAAE_FUSED_STATS", "1") != "0"
         hi = dict(device=self.dev, priority=-1)   # the model's streams outrank the synthesis branch of a pipelined graph
         self.s_branch = [torch.cuda.Stream(**hi) for _ in range(2)] if self.concurrent else []
         self.s_wgrad = [torch.cuda.Stream(**hi) for _ in range(3)] if self.concurrent else []
@@ -351,11 +352,24 @@ class _Engine:
     def _dense_fwd(self, scope, x, ldx, R, training, decay, y, a):
         """y = x W + b; (BN + ReLU -> a) when the layer has BN (tf_util.conv2d 1x1 / fully_connected)."""
         fin, fout, has_bn = self.scopes[scope]
-        self._gemm(0, 0, R, fout, fin, x, ldx, self.v[f"{scope}/weights"], fout, y, fout, self.v[f"{scope}/biases"])
+        W, bias = self.v[f"{scope}/weights"], self.v[f"{scope}/biases"]
+        # tall TF32 contractions followed by training-mode BN (dgcnn_agg, pn_conv5): the persistent GEMM sums the
+        # columns of each output tile while it sits in shared memory, which saves the separate 134 MB statistics pass
+        fused = 0
+        if (has_bn and training and self.fused_stats and self.precision == "tf32" and R * fout * fin >= (1 << 28) and
+                self.lib.caae_gemm_tf32_supported(0, 0, R, fout, fin, self._p(x), ldx, self._p(W), fout)):
+            fused = self.lib.caae_gemm_tf32_stats_parts(R, fout, fin, fout)
+            if fused * 2 * fout > self.parts.numel():
+                fused = 0
+        if fused:
+            self._c("caae_gemm_tf32_stats", R, fout, fin, self._p(x), ldx, self._p(W), fout, self._p(y), fout,
+                    self._p(bias), self._p(self.parts))
+        else:
+            self._gemm(0, 0, R, fout, fin, x, ldx, W, fout, y, fout, bias)
         if has_bn:
-            if training:
+            if training and not fused:
                 self._c("caae_col_stats", R, fout, self._p(y), fout, self._p(self.parts))
-            self._bn_coeffs(scope, training, self.lib.caae_col_parts(R), R, decay)
+            self._bn_coeffs(scope, training, fused if fused else self.lib.caae_col_parts(R), R, decay)
             if a is not None:
                 bn = self.bn[scope]
                 self._c("caae_bn_act", R, fout, self._p(y), fout, self._p(bn["scale"]), self._p(bn["shift"]), 1,

@@ -39,10 +39,10 @@ class SegmentSynthesizer:
         self.points = torch.empty(B, n, 3, **f32)
         self.flip_all = torch.empty(B, n, 3, **f32)
         self.flip_org = torch.empty(B, self.nm, 3, **f32)
-        self.z_centers = torch.empty(B, 2, 3, **f32)
-        self.z_points = torch.empty(B, 2, self.no // 2, 3, **f32)
-        self.pad_u = torch.empty(B, num_point, **f32)
-        self.pad_u_org = torch.empty(B, 4 * num_point, **f32)
+        self.z_centers = torch.zeros(B, 2, 3, **f32)
+        self.z_points = torch.zeros(B, 2, self.no // 2, 3, **f32)
+        self.pad_u = torch.zeros(B, num_point, **f32)       # defined even when synthesize(draw=False) runs first
+        self.pad_u_org = torch.zeros(B, 4 * num_point, **f32)
         # the three products of a batch live in ONE flat buffer so a consumer can take a snapshot with one copy
         self.out_flat = torch.empty(B * 6 * num_point * 3, **f32)
         nv = B * num_point * 3

@@ -101,6 +101,13 @@ int caae_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, i
  * multiples of 4; caae_gemm_tf32_supported() returns 1 when the problem qualifies. */
 int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                    float* C, int ldc, const float* bias, int accumulate, caae_stream_t stream);
+/* caae_gemm_tf32 (no transposes, no accumulate) that ALSO writes the batch-norm column statistics of C while
+ * the output tiles sit in shared memory: parts f64[nparts][2][N] = per partial row the column sums and sums of
+ * squares, the layout caae_bn_finalize reduces.  Only for the tall persistent-kernel shapes:
+ * caae_gemm_tf32_stats_parts returns nparts for a shape, or 0 when the caller has to run caae_col_stats. */
+int caae_gemm_tf32_stats_parts(int M, int N, int K, int ldc);
+int caae_gemm_tf32_stats(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                         const float* bias, double* parts, caae_stream_t stream);
 int caae_gemm_tf32_supported(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
                              int ldb);
 

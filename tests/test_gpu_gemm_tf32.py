@@ -150,3 +150,38 @@ def test_gemm_tf32_big_tile_tma_epilogue(ta, tb, M, N, K):
     torch.cuda.synchronize()
     assert (C[rows].double() - 2 * want).abs().max().item() <= 8e-3 * scale / K ** 0.5
     assert (C[M:] == 7.0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(32768, 1024, 320), (19201, 512, 96), (20000, 1024, 128)])
+def test_gemm_tf32_fused_column_statistics(M, N, K):
+    """caae_gemm_tf32_stats: C as caae_gemm_tf32 writes it, plus per-partial-row column sums and sums of squares
+    of C (bias included, rows past M excluded) in the layout caae_bn_finalize reduces."""
+    lib = _capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator("cuda").manual_seed(7 + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(K, N, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    nparts = lib.caae_gemm_tf32_stats_parts(M, N, K, N)
+    assert nparts == 4 * ((M + 255) // 256)
+    assert lib.caae_gemm_tf32_stats_parts(1000, N, K, N) == 0 and lib.caae_gemm_tf32_stats_parts(M, 320, K, 320) == 0
+    parts = torch.full((nparts, 2, N), float("nan"), dtype=torch.float64, device="cuda")
+    C = torch.empty(M, N, device="cuda")
+    _capi.check(lib.caae_gemm_tf32_stats(M, N, K, A.data_ptr(), K, B.data_ptr(), N, C.data_ptr(), N, bias.data_ptr(),
+                                         parts.data_ptr(), st), "caae_gemm_tf32_stats")
+    C2 = torch.empty(M, N, device="cuda")
+    _run(0, 0, M, N, K, A, K, B, N, C2, N, bias)
+    torch.cuda.synchronize()
+    assert torch.equal(C, C2)                                   # the same kernel, the same arithmetic
+    assert not torch.isnan(parts).any()                          # every partial row written
+    s, q = parts[:, 0].sum(0), parts[:, 1].sum(0)
+    Cd = C.double()
+    want_s, want_q = Cd.sum(0), (Cd * Cd).sum(0)
+    assert (s - want_s).abs().max().item() <= 1e-5 * Cd.abs().sum(0).max().item()
+    assert ((q - want_q).abs() / want_q).max().item() <= 1e-5
+    # mean / variance as the batch norm uses them
+    mean, var = s / M, q / M - (s / M) ** 2
+    assert torch.allclose(mean, Cd.mean(0), atol=1e-6, rtol=1e-5) and torch.allclose(var, Cd.var(0, unbiased=False), rtol=1e-4)
+    # the unsupported cases say so
+    assert lib.caae_gemm_tf32_stats(1000, N, K, A.data_ptr(), K, B.data_ptr(), N, C.data_ptr(), N, None,
+                                    parts.data_ptr(), st) == -4

@@ -263,3 +263,27 @@ def test_cuda_graph_replay_equals_eager():
         assert torch.allclose(le, lg, rtol=1e-6 if it == 0 else 2e-2, atol=1e-6), (it, le, lg)
     assert eager.state[0].item() == graph.state[0].item() == 3
     assert l2_err(v2.flat, v1.flat) < 1e-2
+
+
+def test_fused_gemm_statistics_equal_the_separate_statistics_pass():
+    """At B*N >= 18944 rows the dgcnn_agg forward GEMM sums the batch-norm statistics of its own output tiles
+    (caae_gemm_tf32_stats); the BN coefficients and the losses must equal those of the separate caae_col_stats pass."""
+    b, n = 80, 256
+    v, p64, visible, target, cls, trans, axag, noise = _setup("dgcnn", b, n, seed=9)
+    dev = lambda t: t.cuda().contiguous()  # noqa: E731
+    got = []
+    for fused in (True, False):
+        tr = CloudAAETrainer(batch_size=b, num_point=n, model="dgcnn", variables=v, precision="tf32")
+        tr.engine.fused_stats = fused
+        tr.decay.fill_(0.9)
+        before = _capi.COUNTER[0]
+        losses = tr.forward_losses(dev(visible), dev(target), dev(cls), dev(trans), dev(axag), dev(noise)).clone()
+        launches = _capi.COUNTER[0] - before
+        torch.cuda.synchronize()
+        bn = tr.engine.bn["dgcnn_agg"]
+        got.append((losses, {k: bn[k].clone() for k in ("scale", "shift", "mean", "invstd")}, launches))
+    (l1, bn1, n1), (l0, bn0, n0) = got
+    assert n1 == n0 - 1                                          # the statistics pass is gone
+    for k in bn1:
+        assert torch.allclose(bn1[k], bn0[k], rtol=1e-4, atol=1e-6), k
+    assert torch.allclose(l1, l0, rtol=1e-3, atol=1e-6), (l1, l0)
