@@ -44,7 +44,7 @@ class SegmentSynthesizer:
         self.pad_u = torch.zeros(B, num_point, **f32)       # defined even when synthesize(draw=False) runs first
         self.pad_u_org = torch.zeros(B, 4 * num_point, **f32)
         # the three products of a batch live in ONE flat buffer so a consumer can take a snapshot with one copy
-        self.out_flat = torch.empty(B * 6 * num_point * 3, **f32)
+        self.out_flat = torch.zeros(B * 6 * num_point * 3, **f32)
         nv = B * num_point * 3
         self.visible = self.out_flat[:nv].view(B, num_point, 3)
         self.target = self.out_flat[nv:5 * nv].view(B, 4 * num_point, 3)
