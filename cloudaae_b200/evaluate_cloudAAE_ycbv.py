@@ -63,6 +63,10 @@ class SegmentFrontEnd:
         """segment_not_empty + the masks of outlier_removal.  Returns a dict: xyz_org [S,cap,3], n_org [S],
         xyz_org_distance_filtered [S,cap,3], pix [S,cap] (pixel ids, for rgb), num_point_after_filter [S],
         mean [S,3]."""
+        # host-side lists are range-checked before they reach the kernel (device tensors are the caller's contract)
+        for vals, hi, what in ((frame_of_seg, self.depth.shape[0], "frame"), (class_of_seg, self.thr.shape[0], "class")):
+            if not isinstance(vals, torch.Tensor) and len(vals) and not all(0 <= int(x) < hi for x in vals):
+                raise InvalidArgumentError(f"SegmentFrontEnd.extract: {what} index outside [0, {hi})")
         f = _as_i32(frame_of_seg, self.dev)
         c = _as_i32(class_of_seg, self.dev)
         if f.dim() != 1 or f.shape != c.shape:
