@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcloudaae_b200.so")
 
-ABI_VERSION = 2   # 2: evaluation front end + ICP entry points
+ABI_VERSION = 3   # 3: split-precision forward GEMMs (caae_gemm_tf32x3, caae_split_tf32, caae_edge_apply out_lo)
 
 _int = ctypes.c_int
 _ptr = ctypes.c_void_p
@@ -44,9 +44,11 @@ _SIGNATURES = {
     "caae_gemm_f32": "iiiiipipipipi" "p",
     "caae_gemm_tf32": "iiiiipipipipi" "p",
     "caae_gemm_tf32_stats": "iiipipipipp" "p",
+    "caae_gemm_tf32x3": "iiiiippippipipip" "p",
+    "caae_split_tf32": "lipipi" "p",
     "caae_knn": "iiiipip" "p",
     "caae_edge_stats": "iiiipipp" "p",
-    "caae_edge_apply": "iiiipippppi" "p",
+    "caae_edge_apply": "iiiipippppip" "p",
     "caae_edge_bwd_reduce": "iiiipippppppip" "p",
     "caae_edge_bwd_apply": "iiiipipppppppipi" "p",
     "caae_col_stats": "iipip" "p",
@@ -126,10 +128,12 @@ def lib() -> ctypes.CDLL:
 
 
 COUNTER = [0]  # C-ABI kernel-launching calls issued by this process (each launches >= 1 kernel)
+CALLS: dict = {}  # the same, per entry point (tests assert which kernel family a configuration really took)
 
 
 def check(status: int, what: str) -> None:
     COUNTER[0] += 1
+    CALLS[what] = CALLS.get(what, 0) + 1
     if status != 0:
         msg = lib().caae_status_string(status).decode()
         raise CloudAAENativeError(f"{what} failed with status {status}: {msg}")

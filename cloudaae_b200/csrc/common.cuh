@@ -25,6 +25,14 @@ __device__ __forceinline__ float sqdist_ref(float cx, float cy, float cz, float 
   return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// fp32 -> tf32 (10 explicit mantissa bits), round to nearest even — what the TMA does to a TFLOAT32 tensor map
+// on the way into shared memory (measured: tools/probe_tf32_rounding.py).  x - tf32_rne(x) is exact in fp32.
+__device__ __forceinline__ float tf32_rne(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x0FFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+
 inline cudaStream_t as_stream(caae_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace caae

@@ -143,11 +143,14 @@ struct GemmParams {
   double* stats_parts;  // persistent kernel: per (row tile, lane quadrant) column sums / sums of squares of C (or NULL)
   int tma_store;    // 128 x 128 kernel: 1 = write C with TMA bulk stores from a swizzled staging box (map_c valid),
                     // 2 = C += tile with TMA bulk reductions (accumulate without split-K)
+  int x3;           // split-precision ("3xTF32") product: C = A*B + A_lo*B + A*B_lo with A_lo = A - tf32(A), B_lo likewise
+                    // (map_a_lo / map_b_lo valid) — fp32-grade accuracy at three tensor-core passes
 };
 
 __global__ void __launch_bounds__(TTHREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
   __shared__ __align__(16) float s_bias[TBN];
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-byte alignment
@@ -163,7 +166,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int num_kb_total = (p.K + TBK - 1) / TBK;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-  const int num_kb = kb1 - kb0;
+  const int num_kb_real = kb1 - kb0;
+  // x3: the K loop runs three times over the same K range — (A, B), (A_lo, B), (A, B_lo) — into one accumulator
+  const int num_kb = p.x3 ? 3 * num_kb_real : num_kb_real;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TSTAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -187,19 +192,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t ph = (i / TSTAGES) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, TSTAGE_A + TSTAGE_B);
-        const int k0 = (kb0 + i) * TBK;
+        const int pass = p.x3 ? i / num_kb_real : 0;
+        const int k0 = (kb0 + (i - pass * num_kb_real)) * TBK;
+        const CUtensorMap* ma = (pass == 1) ? &map_a_lo : &map_a;
+        const CUtensorMap* mb = (pass == 2) ? &map_b_lo : &map_b;
         const uint32_t da = smem_a + s * TSTAGE_A, db = smem_b + s * TSTAGE_B;
         if (p.a_mn) {
 #pragma unroll
-          for (int c = 0; c < TBM / 32; ++c) tma_load_2d(da + c * 4096, &map_a, full0 + 8 * s, m0 + 32 * c, k0);
+          for (int c = 0; c < TBM / 32; ++c) tma_load_2d(da + c * 4096, ma, full0 + 8 * s, m0 + 32 * c, k0);
         } else {
-          tma_load_2d(da, &map_a, full0 + 8 * s, k0, m0);
+          tma_load_2d(da, ma, full0 + 8 * s, k0, m0);
         }
         if (p.b_mn) {
 #pragma unroll
-          for (int c = 0; c < TBN / 32; ++c) tma_load_2d(db + c * 4096, &map_b, full0 + 8 * s, n0 + 32 * c, k0);
+          for (int c = 0; c < TBN / 32; ++c) tma_load_2d(db + c * 4096, mb, full0 + 8 * s, n0 + 32 * c, k0);
         } else {
-          tma_load_2d(db, &map_b, full0 + 8 * s, k0, n0);
+          tma_load_2d(db, mb, full0 + 8 * s, k0, n0);
         }
       }
     }
@@ -542,29 +550,45 @@ gemm_tf32_big_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // while the TMA and MMA warps run the main loop of tile i+1, so the output stream — the real bound of a
 // K = 320 GEMM with a 134 MB result — overlaps the tensor work instead of following it.  Barrier set-up,
 // TMEM allocation and descriptor fetch happen once per CTA.  K-major A; B either major; no split-K.
-constexpr int PS_STAGES = 3;
+// X3 = split-precision product (GemmParams::x3): a stage holds FOUR operand tiles (A, B, A_lo, B_lo) and every K step
+// issues three MMAs per row block — A*B, A_lo*B, A*B_lo — so the operand bytes per useful FLOP only double while the
+// result is fp32-grade (the TMA rounds fp32 -> tf32 to nearest-even on the way in: measured, tools/probe_tf32_rounding.py;
+// the low parts A - tf32(A) are prepared by the producers of A / by caae_split_tf32).  Two 96 KB stages, one staging box
+// per epilogue warp, bias read through the read-only path instead of shared memory (227 KB per CTA is the limit).
 constexpr uint32_t PS_STAGE_A = 2 * TSTAGE_A, PS_STAGE_B = TSTAGE_B;
-// epilogue staging: per epilogue warp two 32-row x 128-byte boxes (SWIZZLE_128B, the layout the C tensor map expects)
-constexpr uint32_t PS_STG_BOX = 32 * 128, PS_STG_WARP = 2 * PS_STG_BOX, PS_STG = 8 * PS_STG_WARP;
-constexpr uint32_t PS_SMEM = PS_STAGES * (PS_STAGE_A + PS_STAGE_B) + PS_STG + 1024 + 256;
+// epilogue staging: per epilogue warp 32-row x 128-byte boxes (SWIZZLE_128B, the layout the C tensor map expects)
+constexpr uint32_t PS_STG_BOX = 32 * 128;
 constexpr int PS_MAXN = 2048;
+template <bool X3>
+struct PsCfg {
+  static constexpr int STAGES = X3 ? 2 : 3;
+  static constexpr uint32_t STAGE = (PS_STAGE_A + PS_STAGE_B) * (X3 ? 2u : 1u);
+  static constexpr int BOXES = X3 ? 1 : 2;                       // staging boxes per epilogue warp
+  static constexpr uint32_t STG_WARP = BOXES * PS_STG_BOX, STG = 8 * STG_WARP;
+  static constexpr uint32_t SMEM = STAGES * STAGE + STG + 1024 + 256;
+  static constexpr int BIAS_SMEM = X3 ? 4 : PS_MAXN;
+};
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+template <bool X3>
 __global__ void __launch_bounds__(BIG_THREADS)
 gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         const __grid_constant__ CUtensorMap map_c, const GemmParams p, const int tiles_m,
+                         const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_a_lo,
+                         const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p, const int tiles_m,
                          const int tiles_n) {
-  __shared__ __align__(16) float s_bias[PS_MAXN];
+  using Cfg = PsCfg<X3>;
+  constexpr int ST = Cfg::STAGES;
+  __shared__ __align__(16) float s_bias[Cfg::BIAS_SMEM];
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_a = base, smem_b = base + PS_STAGES * PS_STAGE_A;
-  const uint32_t stg = smem_b + PS_STAGES * PS_STAGE_B;   // 1024-byte aligned: every stage is a multiple of 1 KB
-  const uint32_t bars = stg + PS_STG;
-  const uint32_t full0 = bars, empty0 = bars + 8 * PS_STAGES;
-  const uint32_t tfull0 = empty0 + 8 * PS_STAGES, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+  // stage s: [A (2 row blocks, 32 KB) | B (16 KB) | A_lo | B_lo]
+  const uint32_t stg = base + ST * Cfg::STAGE;   // 1024-byte aligned: every stage is a multiple of 1 KB
+  const uint32_t bars = stg + Cfg::STG;
+  const uint32_t full0 = bars, empty0 = bars + 8 * ST;
+  const uint32_t tfull0 = empty0 + 8 * ST, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -572,7 +596,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   const int tiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PS_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < ST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -580,7 +604,8 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int t = threadIdx.x; t < p.N; t += BIG_THREADS) s_bias[t] = (p.bias != nullptr) ? p.bias[t] : 0.f;
+  if (!X3)
+    for (int t = threadIdx.x; t < p.N; t += BIG_THREADS) s_bias[t] = (p.bias != nullptr) ? p.bias[t] : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -594,19 +619,25 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       for (int id = blockIdx.x; id < tiles; id += gridDim.x) {
         const int m0 = (id / tiles_n) * (2 * TBM), n0 = (id % tiles_n) * TBN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % PS_STAGES;
-          const uint32_t ph = (it / PS_STAGES) & 1;
+          const int s = it % ST;
+          const uint32_t ph = (it / ST) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
-          mbar_expect_tx(full0 + 8 * s, PS_STAGE_A + PS_STAGE_B);
+          mbar_expect_tx(full0 + 8 * s, Cfg::STAGE);
           const int k0 = kb * TBK;
-          const uint32_t da = smem_a + s * PS_STAGE_A, db = smem_b + s * PS_STAGE_B;
-          tma_load_2d(da, &map_a, full0 + 8 * s, k0, m0);
-          tma_load_2d(da + TSTAGE_A, &map_a, full0 + 8 * s, k0, m0 + TBM);
-          if (p.b_mn) {
+          const uint32_t da = base + s * Cfg::STAGE, db = da + PS_STAGE_A;
 #pragma unroll
-            for (int c = 0; c < TBN / 32; ++c) tma_load_2d(db + c * 4096, &map_b, full0 + 8 * s, n0 + 32 * c, k0);
-          } else {
-            tma_load_2d(db, &map_b, full0 + 8 * s, k0, n0);
+          for (int v = 0; v < (X3 ? 2 : 1); ++v) {
+            const CUtensorMap* ma = v ? &map_a_lo : &map_a;
+            const CUtensorMap* mb = v ? &map_b_lo : &map_b;
+            const uint32_t dav = da + v * (PS_STAGE_A + PS_STAGE_B), dbv = db + v * (PS_STAGE_A + PS_STAGE_B);
+            tma_load_2d(dav, ma, full0 + 8 * s, k0, m0);
+            tma_load_2d(dav + TSTAGE_A, ma, full0 + 8 * s, k0, m0 + TBM);
+            if (p.b_mn) {
+#pragma unroll
+              for (int c = 0; c < TBN / 32; ++c) tma_load_2d(dbv + c * 4096, mb, full0 + 8 * s, n0 + 32 * c, k0);
+            } else {
+              tma_load_2d(dbv, mb, full0 + 8 * s, k0, n0);
+            }
           }
         }
       }
@@ -623,18 +654,25 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + (uint32_t)(acc * 256);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % PS_STAGES;
-          const uint32_t ph = (it / PS_STAGES) & 1;
+          const int s = it % ST;
+          const uint32_t ph = (it / ST) & 1;
           mbar_wait(full0 + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t da = smem_a + s * PS_STAGE_A, db = smem_b + s * PS_STAGE_B;
+          const uint32_t da = base + s * Cfg::STAGE, db = da + PS_STAGE_A;
+          constexpr uint32_t LO = PS_STAGE_A + PS_STAGE_B;
 #pragma unroll
           for (int k = 0; k < TBK / 8; ++k) {
             const uint64_t bdesc = make_smem_desc(db + k * b_kstep, b_lbo, b_sbo, b_lt);
+            const uint64_t bdesc_lo = make_smem_desc(db + LO + k * b_kstep, b_lbo, b_sbo, b_lt);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint64_t adesc = make_smem_desc(da + h * TSTAGE_A + k * 32u, 16u, 1024u, 2u);
               umma_tf32(tacc + (uint32_t)(h * TBN), adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
+              if (X3) {
+                const uint64_t adesc_lo = make_smem_desc(da + LO + h * TSTAGE_A + k * 32u, 16u, 1024u, 2u);
+                umma_tf32(tacc + (uint32_t)(h * TBN), adesc_lo, bdesc, p.idesc, 1u);
+                umma_tf32(tacc + (uint32_t)(h * TBN), adesc, bdesc_lo, p.idesc, 1u);
+              }
             }
           }
           umma_commit(empty0 + 8 * s);
@@ -655,21 +693,25 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
       auto taddr = [&](int w) { return tlane + (uint32_t)((w / NC) * TBN + (w % NC) * 32); };
       double st_sum[2] = {0.0, 0.0}, st_sq[2] = {0.0, 0.0};   // this warp's two column chunks (part, part + 2), both row blocks
+      auto bias4 = [&](int col) -> float4 {
+        if (X3) return p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return *reinterpret_cast<const float4*>(s_bias + col);
+      };
       auto store_item = [&](uint32_t (&r)[32], int w) {
         const int h = w / NC, c0 = (w % NC) * 32;
         if (!p.accumulate) {
           // registers -> swizzled shared-memory box -> one TMA store of 32 rows x 128 bytes (full lines; rows past M
           // are clipped by the tensor map).  A thread-per-row STG.128 writes 16 bytes to 32 different lines per
           // instruction: that, not the tensor pipe, bounded this kernel (134 MB at 1.9 TB/s).
-          const uint32_t box = stg + (uint32_t)(warp - 2) * PS_STG_WARP + (uint32_t)sbuf * PS_STG_BOX;
-          if (lane == 0) tma_store_wait_read<1>();   // the store that last read this box (two items ago) is done with it
+          const uint32_t box = stg + (uint32_t)(warp - 2) * Cfg::STG_WARP + (uint32_t)sbuf * PS_STG_BOX;
+          if (lane == 0) tma_store_wait_read<Cfg::BOXES - 1>();   // the store that last read this box is done with it
           __syncwarp();
           const uint32_t rowaddr = box + (uint32_t)lane * 128u;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                    __uint_as_float(r[j + 3]));
-            const float4 bv = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + j);
+            const float4 bv = bias4(n0 + c0 + j);
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
             st_shared_v4(rowaddr + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4), v);   // SWIZZLE_128B: chunk ^= row % 8
           }
@@ -695,7 +737,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             st_sum[slot] += (double)fs;
             st_sq[slot] += (double)fq;
           }
-          sbuf ^= 1;
+          if (Cfg::BOXES == 2) sbuf ^= 1;
           return;
         }
         const int row = m0 + h * TBM + quad * 32 + lane;
@@ -705,7 +747,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         for (int j = 0; j < 32; j += 4) {
           float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                  __uint_as_float(r[j + 3]));
-          const float4 bv = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + j);
+          const float4 bv = bias4(n0 + c0 + j);
           v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           const float4 o = *reinterpret_cast<const float4*>(crow + j);
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -747,6 +789,17 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// lo = x - tf32_rne(x): the low part of a split-precision operand (exact in fp32).  [rows, cols] with row pitches.
+__global__ void split_tf32_kernel(long rows, int cols, const float* __restrict__ x, int ldx, float* __restrict__ lo, int ldlo) {
+  const long total = rows * cols;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long r = e / cols;
+    const int c = (int)(e - r * cols);
+    const float v = x[r * ldx + c];
+    lo[r * ldlo + c] = v - tf32_rne(v);
   }
 }
 
@@ -819,15 +872,18 @@ extern "C" int caae_gemm_tf32_supported(int transa, int transb, int M, int N, in
 
 static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
                           int ldb, float* C, int ldc, const float* bias, int accumulate, double* stats_parts,
-                          caae_stream_t stream) {
+                          caae_stream_t stream, const float* A_lo = nullptr, const float* B_lo = nullptr) {
   CAAE_RETURN_IF(M < 0 || N < 0 || K < 0, CAAE_E_BADSHAPE);
   if (M == 0 || N == 0) return CAAE_OK;
   CAAE_RETURN_IF(!C || !A || !B, CAAE_E_NULLPTR);
   CAAE_RETURN_IF(ldc < N || lda < (transa ? M : K) || ldb < (transb ? K : N), CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!caae_gemm_tf32_supported(transa, transb, M, N, K, A, lda, B, ldb), CAAE_E_UNSUPPORTED);
+  const bool x3 = A_lo != nullptr || B_lo != nullptr;
+  CAAE_RETURN_IF(x3 && (!A_lo || !B_lo), CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(x3 && ((reinterpret_cast<uintptr_t>(A_lo) & 15) || (reinterpret_cast<uintptr_t>(B_lo) & 15)), CAAE_E_UNSUPPORTED);
   cudaStream_t s = as_stream(stream);
 
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_a_lo, map_b_lo;
   int rc;
   // A: transa = 0 -> stored [M,K] (K contiguous, K-major); transa = 1 -> stored [K,M] (M contiguous, MN-major)
   rc = transa ? make_map(&map_a, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK, true)
@@ -837,8 +893,18 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
   rc = transb ? make_map(&map_b, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, TBN, false)
               : make_map(&map_b, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
   if (rc) return rc;
+  map_a_lo = map_a; map_b_lo = map_b;   // placeholders unless the split-precision product is requested
+  if (x3) {   // the low parts share the layout (and leading dimension) of their operand
+    rc = transa ? make_map(&map_a_lo, A_lo, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK, true)
+                : make_map(&map_a_lo, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
+    if (rc) return rc;
+    rc = transb ? make_map(&map_b_lo, B_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, TBN, false)
+                : make_map(&map_b_lo, B_lo, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
+    if (rc) return rc;
+  }
 
   GemmParams p;
+  p.x3 = x3 ? 1 : 0;
   p.tma_store = 0;
   p.stats_parts = nullptr;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
@@ -867,7 +933,11 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
     if (rc) return rc;
     static bool psattr = false;
     if (!psattr) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM);
+      cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)PsCfg<false>::SMEM);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(gemm_tf32_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)PsCfg<true>::SMEM);
       if (e != cudaSuccess) return (int)e;
       psattr = true;
     }
@@ -877,15 +947,18 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
     const int tm = (M + 2 * TBM - 1) / (2 * TBM), tn = N / TBN;
     p.kb_per_split = num_kb; p.atomic = 0; p.accumulate = accumulate;
     const int ctas = tm * tn < kNumSMs ? tm * tn : kNumSMs;
-    gemm_tf32_persist_kernel<<<ctas, BIG_THREADS, PS_SMEM, s>>>(map_a2, map_b2, map_c2, p, tm, tn);
+    if (x3)   // (the *_lo maps built above have the same boxes as map_a2 / map_b2: K-major A, either-major B)
+      gemm_tf32_persist_kernel<true><<<ctas, BIG_THREADS, PsCfg<true>::SMEM, s>>>(map_a2, map_b2, map_c2, map_a_lo, map_b_lo, p, tm, tn);
+    else
+      gemm_tf32_persist_kernel<false><<<ctas, BIG_THREADS, PsCfg<false>::SMEM, s>>>(map_a2, map_b2, map_c2, map_a2, map_b2, p, tm, tn);
     return CAAE_LAUNCH_STATUS();
   }
   // the three big dgcnn_agg-shaped contractions: large tiles, one CTA per SM (see gemm_tf32_big_kernel)
   static const bool big_enabled = [] { const char* e = getenv("CAAE_GEMM_BIG"); return !(e && e[0] == '0'); }();
   // (N % 256 == 0 shapes such as the dgcnn_agg forward GEMM stay on the 128 x 128 kernel: measured 85 us vs
   // 94 us for a 256 x 256 tile, whose serial epilogue of 256 KB per tile outweighs the saved operand traffic)
-  const bool big_fwd = !transa && M >= 256 * kNumSMs / 2 && K >= 256 && N >= 160 && N % 160 == 0 && N % 256 != 0;
-  const bool big_wgrad = transa && !transb && M > 256 && M <= 384 && N % 128 == 0 && N >= 512 && K >= 64 * TBK * 8;
+  const bool big_fwd = !x3 && !transa && M >= 256 * kNumSMs / 2 && K >= 256 && N >= 160 && N % 160 == 0 && N % 256 != 0;
+  const bool big_wgrad = !x3 && transa && !transb && M > 256 && M <= 384 && N % 128 == 0 && N >= 512 && K >= 64 * TBK * 8;
   if (big_enabled && (big_fwd || big_wgrad)) {
     const int bn = big_wgrad ? 128 : 160;
     const int mh = big_wgrad ? 3 : 2;
@@ -937,7 +1010,7 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
   }
   int splits = 1;
   const int tiles = tiles_m * tiles_n;
-  if (tiles < kNumSMs && num_kb >= 8) {
+  if (tiles < kNumSMs && num_kb >= 8 && !x3) {   // (the three passes of an x3 product share one accumulator: no split-K)
     splits = (2 * kNumSMs + tiles - 1) / tiles;
     // >= 16 K blocks per split when K is long: with 147 splits of 7 blocks the [64,256] EdgeConv weight gradient
     // spent its time in prologues and in 147-way contended reductions (57 us for 1 GFLOP)
@@ -971,13 +1044,33 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
     if (rc) return rc;
     p.tma_store = p.accumulate ? 2 : 1;
   }
-  gemm_tf32_kernel<<<grid, TTHREADS, TSMEM_BYTES, s>>>(map_a, map_b, map_c, p);
+  gemm_tf32_kernel<<<grid, TTHREADS, TSMEM_BYTES, s>>>(map_a, map_b, map_c, map_a_lo, map_b_lo, p);
   return CAAE_LAUNCH_STATUS();
 }
 
 extern "C" int caae_gemm_tf32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
                               int ldb, float* C, int ldc, const float* bias, int accumulate, caae_stream_t stream) {
   return gemm_tf32_impl(transa, transb, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, nullptr, stream);
+}
+
+// Split-precision variant: C (+)= A*B + A_lo*B + A*B_lo (+ bias) with the low parts x - tf32(x) supplied by the caller
+// (caae_split_tf32, or the producing kernel).  parts != NULL: also the batch-norm column statistics (persistent shapes).
+extern "C" int caae_gemm_tf32x3(int transa, int transb, int M, int N, int K, const float* A, const float* A_lo, int lda,
+                                const float* B, const float* B_lo, int ldb, float* C, int ldc, const float* bias,
+                                int accumulate, double* parts, caae_stream_t stream) {
+  CAAE_RETURN_IF(!A_lo || !B_lo, CAAE_E_NULLPTR);
+  return gemm_tf32_impl(transa, transb, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, parts, stream, A_lo, B_lo);
+}
+
+extern "C" int caae_split_tf32(long rows, int cols, const float* x, int ldx, float* lo, int ldlo, caae_stream_t stream) {
+  CAAE_RETURN_IF(rows < 0 || cols <= 0 || ldx < cols || ldlo < cols, CAAE_E_BADSHAPE);
+  if (rows == 0) return CAAE_OK;
+  CAAE_RETURN_IF(!x || !lo, CAAE_E_NULLPTR);
+  const long total = rows * cols;
+  long blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  split_tf32_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(rows, cols, x, ldx, lo, ldlo);
+  return CAAE_LAUNCH_STATUS();
 }
 
 // Partial rows caae_gemm_tf32_stats writes for this shape (0: the fused-statistics path does not apply).

@@ -81,7 +81,8 @@ edge_reduce_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldp
 // out[i][ch] = (1/k) sum_j relu(z_ij*scale + shift)
 __global__ void __launch_bounds__(256)
 edge_apply_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq, const int* __restrict__ idx,
-                  const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ldo) {
+                  const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ldo,
+                  float* __restrict__ out_lo) {
   __shared__ int s_idx[EDGE_PTS * 32];
   const int cloud = blockIdx.y, p0 = blockIdx.x * EDGE_PTS;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
@@ -99,7 +100,9 @@ edge_apply_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
         const float z = pv + PQ[(base + s_idx[p * k + j]) * ldpq + cout + ch];
         acc += fmaxf(fmaf(z, sc, sh), 0.f);
       }
-      out[(base + p0 + p) * ldo + ch] = acc * invk;
+      const float v = acc * invk;
+      out[(base + p0 + p) * ldo + ch] = v;
+      if (out_lo != nullptr) out_lo[(base + p0 + p) * ldo + ch] = v - tf32_rne(v);
     }
   }
 }
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(1024)
 edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq, const int* __restrict__ idx,
                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef, const float* __restrict__ dOut,
-                  int lddo, float* __restrict__ out, int ldo, double* __restrict__ parts) {
+                  int lddo, float* __restrict__ out, int ldo, double* __restrict__ parts, float* __restrict__ out_lo) {
   extern __shared__ __align__(16) float es_smem[];
   float* Qs = es_smem;                                   // [n][ES_CH]
   float* dQs = Qs + (size_t)n * ES_CH;                   // [n][ES_CH] (MODE 3 only)
@@ -598,7 +601,15 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
         if (MODE == 0) { a[c] += (double)fa[c]; b[c] += (double)fb[c]; }
         if (MODE == 2) { a[c] += (double)(g[c] * fa[c]); b[c] += (double)(g[c] * fb[c]); }
       }
-      if (MODE == 1) { float* op = out + (base + p) * ldo + ch; op[0] = acc[0] * invk; op[1] = acc[1] * invk; }
+      if (MODE == 1) {
+        float* op = out + (base + p) * ldo + ch;
+        const float v0 = acc[0] * invk, v1 = acc[1] * invk;
+        op[0] = v0; op[1] = v1;
+        if (out_lo != nullptr) {   // low part for the split-precision GEMMs that read this activation (same pitch)
+          float* lp = out_lo + (base + p) * ldo + ch;
+          lp[0] = v0 - tf32_rne(v0); lp[1] = v1 - tf32_rne(v1);
+        }
+      }
       if (MODE == 3) *reinterpret_cast<float2*>(out + (base + p) * ldo + ch) = make_float2(acc[0], acc[1]);  // dP
     }
     if (MODE == 0 || MODE == 2) {
@@ -639,14 +650,14 @@ template <int MODE>
 static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
                              const float* scale, const float* shift, const float* mean, const float* invstd,
                              const float* coef, const float* dOut, int lddo, float* out, int ldo, double* parts,
-                             cudaStream_t s) {
+                             cudaStream_t s, float* out_lo = nullptr) {
   const size_t smem = edge_cloud_smem(n, k, MODE);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(edge_cloud_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
   edge_cloud_kernel<MODE><<<dim3(cout / ES_CH, b), dim3(32, 32), smem, s>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean,
-                                                                          invstd, coef, dOut, lddo, out, ldo, parts);
+                                                                          invstd, coef, dOut, lddo, out, ldo, parts, out_lo);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -688,17 +699,18 @@ extern "C" int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, i
 }
 
 extern "C" int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
-                               const float* scale, const float* shift, float* out, int ldo, caae_stream_t stream) {
+                               const float* scale, const float* shift, float* out, int ldo, float* out_lo,
+                               caae_stream_t stream) {
   CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout || ldo < cout, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!PQ || !idx || !scale || !shift || !out, CAAE_E_NULLPTR);
   if (edge_cloud_ok(n, k, cout, ldpq)) {
     CAAE_RETURN_IF(!aligned16(PQ), CAAE_E_UNSUPPORTED);
     return launch_edge_cloud<1>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out,
-                                ldo, nullptr, as_stream(stream));
+                                ldo, nullptr, as_stream(stream), out_lo);
   }
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
-  edge_apply_kernel<<<grid, block, 0, as_stream(stream)>>>(n, k, cout, PQ, ldpq, idx, scale, shift, out, ldo);
+  edge_apply_kernel<<<grid, block, 0, as_stream(stream)>>>(n, k, cout, PQ, ldpq, idx, scale, shift, out, ldo, out_lo);
   return CAAE_LAUNCH_STATUS();
 }
 

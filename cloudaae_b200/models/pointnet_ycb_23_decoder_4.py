@@ -173,11 +173,13 @@ class _Engine:
             self.couts = [64, 64, 64, 128]
             self.offs = [0, 64, 128, 192]
             self.hcat = torch.empty(R, 320, **f32)
+            self.hcat_lo = torch.empty(R, 320, **f32)   # hcat - tf32(hcat): low part for the split-precision forward GEMMs
             self.d_hcat = torch.empty(R, 320, **f32)
             self.idx = [torch.empty(R, k, dtype=torch.int32, device=self.dev) for _ in range(4)]
             self.pq = [torch.empty(R, 2 * c, **f32) for c in self.couts]
             self.d_pq = [torch.empty(R, 2 * c, **f32) for c in self.couts]   # per layer: wgrad of layer l overlaps layer l-1
             self.wf = [torch.empty(ci, 2 * co, **f32) for ci, co in zip(self.cins, self.couts)]
+            self.wf_lo = [torch.empty(ci, 2 * co, **f32) for ci, co in zip(self.cins, self.couts)]
             self.bf = [torch.empty(2 * co, **f32) for co in self.couts]
             self.d_wf = [torch.empty(ci, 2 * co, **f32) for ci, co in zip(self.cins, self.couts)]
             self.yagg = torch.empty(R, 1024, **f32)
@@ -188,6 +190,11 @@ class _Engine:
             self.enc_a = [torch.empty(R, self.scopes[s][1], **f32) for s in self.enc[:-1]]
             self.enc_d = [torch.empty(R, self.scopes[s][1], **f32) for s in self.enc[:-1]]
             self.argmax = torch.empty(B, 1024, dtype=torch.int32, device=self.dev)
+        # low parts of the forward-GEMM operands that no producer kernel writes directly (weights; pn activations)
+        conv_scopes = ["dgcnn_agg"] if model == "dgcnn" else self.enc
+        self.w_lo = {s_: torch.empty(self.scopes[s_][0], self.scopes[s_][1], **f32) for s_ in conv_scopes
+                     if R * self.scopes[s_][0] * self.scopes[s_][1] >= (1 << 28)}
+        self.a_lo = {}
         p = "dgcnn" if model == "dgcnn" else "pn"
         self.prefix = p
         fc1, fc2, out = (f"{p}_fc1", f"{p}_fc2", f"{p}_output") if p == "dgcnn" else \
@@ -224,6 +231,8 @@ class _Engine:
         # is far too small to fill 148 SMs on its own.  CLOUDAAE_STREAMS=0 serialises everything.
         self.concurrent = os.environ.get("CLOUDAAE_STREAMS", "1") != "0" and self.dev.type == "cuda"
         self.fused_stats = os.environ.get("CLOUDAAE_FUSED_STATS", "1") != "0"
+        # forward GEMMs on the tensor cores: split-precision by default (CLOUDAAE_TF32X3=0: single TF32 pass)
+        self.x3 = self.precision == "tf32" and os.environ.get("CLOUDAAE_TF32X3", "1") != "0"
         hi = dict(device=self.dev, priority=-1)   # the model's streams outrank the synthesis branch of a pipelined graph
         self.s_branch = [torch.cuda.Stream(**hi) for _ in range(2)] if self.concurrent else []
         self.s_wgrad = [torch.cuda.Stream(**hi) for _ in range(3)] if self.concurrent else []
@@ -328,13 +337,33 @@ class _Engine:
         weight-bandwidth bound, and its batch-norm backward over only `batch` rows amplifies TF32
         rounding of the pre-activations far beyond the 1e-3 parity budget."""
         fn = "caae_gemm_f32"
+        if self._tensor_core(ta, tb, M, N, K, A, lda, Bm, ldb):
+            fn = "caae_gemm_tf32"
+        self._c(fn, ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), acc)
+
+    def _tensor_core(self, ta, tb, M, N, K, A, lda, Bm, ldb):
         # large contractions only (>= 2^28 MACs with >= 64 output columns): besides dgcnn_agg these are the
         # EdgeConv projections and their data / weight gradients (M or K = B*N rows)
         # (never the FC stack: none of its dimensions is the B*N row count)
-        if (self.precision == "tf32" and M * N * K >= (1 << 28) and N >= 64 and max(M, K) >= 8192 and
-                self.lib.caae_gemm_tf32_supported(ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb)):
-            fn = "caae_gemm_tf32"
-        self._c(fn, ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), acc)
+        return bool(self.precision == "tf32" and M * N * K >= (1 << 28) and N >= 64 and max(M, K) >= 8192 and
+                    self.lib.caae_gemm_tf32_supported(ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb))
+
+    def _split(self, x, ldx, rows, cols, lo, ldlo):
+        """lo = x - tf32(x): the low part of a split-precision GEMM operand."""
+        self._c("caae_split_tf32", rows, cols, self._p(x), ldx, self._p(lo), ldlo)
+
+    def _gemm_fwd(self, M, N, K, A, A_lo, lda, Bm, B_lo, ldb, C, ldc, bias, parts=None):
+        """Forward contraction C = A B + bias.  On the tensor cores it is the split-precision product
+        (caae_gemm_tf32x3: A B + A_lo B + A B_lo): a single TF32 pass perturbs the encoder features by ~5e-4, which
+        the batch norm over the batch axis of the FC layers amplifies beyond the 1e-3 parity budget of the pose
+        outputs (measured at B = 128: rot 2.1e-3, gradients 2e-2), and flips 6-14 % of the layer 3/4 neighbours.
+        Returns True when the tensor-core path (and `parts`, if given) was taken."""
+        if self.x3 and A_lo is not None and B_lo is not None and self._tensor_core(0, 0, M, N, K, A, lda, Bm, ldb):
+            self._c("caae_gemm_tf32x3", 0, 0, M, N, K, self._p(A), self._p(A_lo), lda, self._p(Bm), self._p(B_lo), ldb,
+                    self._p(C), ldc, self._p(bias), 0, self._p(parts))
+            return True
+        self._gemm(0, 0, M, N, K, A, lda, Bm, ldb, C, ldc, bias)
+        return False
 
     def _bn_coeffs(self, scope, training, nparts, count, decay):
         v, bn = self.v, self.bn[scope]
@@ -349,7 +378,7 @@ class _Engine:
                     self._p(v[f"{scope}/bn/ema_mean"]), self._p(v[f"{scope}/bn/ema_var"]), self._p(bn["scale"]),
                     self._p(bn["shift"]))
 
-    def _dense_fwd(self, scope, x, ldx, R, training, decay, y, a):
+    def _dense_fwd(self, scope, x, ldx, R, training, decay, y, a, x_lo=None):
         """y = x W + b; (BN + ReLU -> a) when the layer has BN (tf_util.conv2d 1x1 / fully_connected)."""
         fin, fout, has_bn = self.scopes[scope]
         W, bias = self.v[f"{scope}/weights"], self.v[f"{scope}/biases"]
@@ -361,7 +390,15 @@ class _Engine:
             fused = self.lib.caae_gemm_tf32_stats_parts(R, fout, fin, fout)
             if fused * 2 * fout > self.parts.numel():
                 fused = 0
-        if fused:
+        if self.x3 and scope in self.w_lo and self._tensor_core(0, 0, R, fout, fin, x, ldx, W, fout):
+            if x_lo is None:   # no producer wrote the low part of this activation: one elementwise pass
+                if scope not in self.a_lo:
+                    self.a_lo[scope] = torch.empty(R, fin, dtype=torch.float32, device=self.dev)
+                x_lo = self.a_lo[scope]
+                self._split(x, ldx, R, fin, x_lo, fin)
+            self._gemm_fwd(R, fout, fin, x, x_lo, ldx, W, self.w_lo[scope], fout, y, fout, bias,
+                           self.parts if fused else None)
+        elif fused:
             self._c("caae_gemm_tf32_stats", R, fout, fin, self._p(x), ldx, self._p(W), fout, self._p(y), fout,
                     self._p(bias), self._p(self.parts))
         else:
@@ -408,19 +445,27 @@ class _Engine:
         if se is not None: self._fork(se)
         with self._on(se):   # accumulation targets of the FC stack's split-K GEMMs (forward and backward)
             self._c("caae_fill_f32", self.fc_acc_flat.numel(), self._p(self.fc_acc_flat), 0.0)
+            if self.x3:          # low parts of the conv weights that take the split-precision tensor-core product
+                for s_, lo in self.w_lo.items():
+                    fin_, fout_, _ = self.scopes[s_]
+                    self._split(self.v[f"{s_}/weights"], fout_, fin_, fout_, lo, fout_)
         if self.model == "dgcnn":
-            feat, ldf, cknn = x, D, 3
-            with self._on(se):   # the folded weights depend on the parameters only
+            feat, feat_lo, ldf, cknn = x, None, D, 3
+            with self._on(se):   # the folded weights (and the low parts of the weights) depend on the parameters only
                 for l in range(4):
                     self._c("caae_edge_fold_weights", self.cins[l], self.couts[l], self._p(self.v[f"dgcnn{l + 1}/weights"]),
                             self._p(self.v[f"dgcnn{l + 1}/biases"]), self._p(self.wf[l]), self._p(self.bf[l]), self.couts[l])
+                    if self.x3 and l > 0:
+                        self._split(self.wf[l], 2 * self.couts[l], self.cins[l], 2 * self.couts[l], self.wf_lo[l], 2 * self.couts[l])
+
             for l in range(4):
                 scope = f"dgcnn{l + 1}"
                 ci, co = self.cins[l], self.couts[l]
                 # the projection [P|Q] = X Wf and the kNN search read the same features: run them side by side
                 if se is not None: self._fork(se)
                 with self._on(se):
-                    self._gemm(0, 0, R, 2 * co, ci, feat, ldf, self.wf[l], 2 * co, self.pq[l], 2 * co, self.bf[l])
+                    self._gemm_fwd(R, 2 * co, ci, feat, feat_lo, ldf, self.wf[l], self.wf_lo[l], 2 * co, self.pq[l], 2 * co,
+                                   self.bf[l])
                 self._c("caae_knn", B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
                 if se is not None: self._join(se)
                 if train_enc:
@@ -428,12 +473,14 @@ class _Engine:
                             self._p(self.parts))
                 self._bn_coeffs(scope, train_enc, self.lib.caae_edge_parts(B, N, k, co, 2 * co), R * k, decay)
                 out = self.hcat[:, self.offs[l]:]
+                feat_lo = self.hcat_lo[:, self.offs[l]:] if self.x3 else None   # written by the same kernel
                 bn = self.bn[scope]
                 self._c("caae_edge_apply", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
-                        self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320)
+                        self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320, self._p(feat_lo))
                 feat, ldf, cknn = out, 320, co
             scope = "dgcnn_agg"
-            self._dense_fwd(scope, self.hcat, 320, R, train_enc, decay, self.yagg, None)
+            self._dense_fwd(scope, self.hcat, 320, R, train_enc, decay, self.yagg, None,
+                            x_lo=self.hcat_lo if self.x3 else None)
             bn = self.bn[scope]
             self._c("caae_bn_act_pool", B, N, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]),
                     self._p(bn["shift"]), 0, self._p(self.emb), None)
@@ -560,7 +607,7 @@ def reset_default_variables():
 
 
 def _engine_for(variables: Variables, model: str, b: int, n: int, d: int, k: int) -> _Engine:
-    key = (id(variables), model, b, n, d, k, os.environ.get("CLOUDAAE_GEMM", "tf32"))
+    key = (id(variables), model, b, n, d, k, os.environ.get("CLOUDAAE_GEMM", "tf32"), os.environ.get("CLOUDAAE_TF32X3", "1"))
     if key not in _ENGINES:
         _ENGINES[key] = _Engine(variables, model, b, n, d, k)
     return _ENGINES[key]

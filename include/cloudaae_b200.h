@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CAAE_ABI_VERSION 2
+#define CAAE_ABI_VERSION 3
 
 /* argument errors (negative); positive return values are cudaError_t */
 #define CAAE_OK 0
@@ -110,6 +110,16 @@ int caae_gemm_tf32_stats(int M, int N, int K, const float* A, int lda, const flo
                          const float* bias, double* parts, caae_stream_t stream);
 int caae_gemm_tf32_supported(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
                              int ldb);
+/* Split-precision ("3xTF32") product for the FORWARD contractions whose rounding reaches the pose outputs:
+ * C (+)= A*B + A_lo*B + A*B_lo (+ bias), A_lo = A - tf32(A) and B_lo = B - tf32(B) (same layouts and leading
+ * dimensions as A, B; made by caae_split_tf32 or by the kernel that produced the operand).  Three tensor-core
+ * passes into one TMEM accumulator; relative error ~1e-6 instead of ~5e-4 (the reference computes these
+ * tf.matmul / conv2d in fp32, utils/tf_util.py:161,349).  parts != NULL as in caae_gemm_tf32_stats. */
+int caae_gemm_tf32x3(int transa, int transb, int M, int N, int K, const float* A, const float* A_lo, int lda,
+                     const float* B, const float* B_lo, int ldb, float* C, int ldc, const float* bias, int accumulate,
+                     double* parts, caae_stream_t stream);
+/* lo[r][c] = x[r][c] - tf32_round_to_nearest_even(x[r][c])  (exact in fp32) */
+int caae_split_tf32(long rows, int cols, const float* x, int ldx, float* lo, int ldlo, caae_stream_t stream);
 
 /* pairwise_xyz_distance + knn (tf_util.py:597-632): x [b*n, ldx] (first c channels), idx i32[b*n,k],
  * k smallest of (|xi|^2 - 2 xi.xj) + |xj|^2, ascending, ties to the lower index, self included. */
@@ -122,8 +132,9 @@ int caae_edge_fold_weights(int c, int cout, const float* w, const float* bias, f
 int caae_edge_unfold_wgrad(int c, int cout, const float* dwf, int lddwf, float* dw, caae_stream_t stream);
 int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, double* parts,
                     caae_stream_t stream);
+/* out_lo (may be NULL): out - tf32(out) with the pitch of out, the low part caae_gemm_tf32x3 reads */
 int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const float* scale,
-                    const float* shift, float* out, int ldo, caae_stream_t stream);
+                    const float* shift, float* out, int ldo, float* out_lo, caae_stream_t stream);
 int caae_edge_bwd_reduce(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
                          const float* scale, const float* shift, const float* mean, const float* invstd,
                          const float* dOut, int lddo, double* parts, caae_stream_t stream);

@@ -185,3 +185,58 @@ def test_gemm_tf32_fused_column_statistics(M, N, K):
     # the unsupported cases say so
     assert lib.caae_gemm_tf32_stats(1000, N, K, A.data_ptr(), K, B.data_ptr(), N, C.data_ptr(), N, None,
                                     parts.data_ptr(), st) == -4
+
+
+# ---- split-precision ("3xTF32") forward product ---------------------------------------------------------------
+def _split(x):
+    lo = torch.empty_like(x)
+    rows, cols = x.shape
+    _capi.check(_capi.lib().caae_split_tf32(rows, cols, x.data_ptr(), cols, lo.data_ptr(), cols,
+                                            torch.cuda.current_stream().cuda_stream), "caae_split_tf32")
+    return lo
+
+
+def test_split_tf32_is_exact_and_round_to_nearest_even():
+    x = torch.tensor([[1 + 3 * 2.0 ** -12, 1 + 2.0 ** -11, 1 + 2.0 ** -10 + 2.0 ** -11, -(1 + 3 * 2.0 ** -12), 0.0, 3.14159274]],
+                     device="cuda")
+    lo = _split(x)
+    hi = x - lo
+    assert (hi.view(torch.int32) & 0x1FFF == 0).all()                       # hi is a tf32 number
+    assert torch.equal(hi + lo, x)                                          # the split is exact
+    want_hi = torch.tensor([[1 + 2.0 ** -10, 1.0, 1 + 2.0 ** -9, -(1 + 2.0 ** -10), 0.0, 3.140625]], device="cuda")
+    assert torch.equal(hi, want_hi)
+
+
+@pytest.mark.parametrize("M,N,K,tb,stats", [(32768, 1024, 320, 0, True), (32768, 1024, 320, 0, False), (19201, 512, 96, 0, True),
+                                            (32768, 128, 64, 0, False), (32768, 256, 64, 0, False), (4096, 1024, 128, 1, False),
+                                            (300, 130, 77, 0, False)])
+def test_gemm_tf32x3_is_fp32_grade(M, N, K, tb, stats):
+    """A*B + A_lo*B + A*B_lo on the tensor cores vs float64: relative error ~1e-6 (one TF32 pass: ~5e-4).
+    Shapes: dgcnn_agg forward (persistent kernel, with and without fused BN statistics), ragged rows, the EdgeConv
+    projections (128 x 128 kernel, K = 64), a K-major B, and odd tails."""
+    g = torch.Generator("cuda").manual_seed(3 * M + N + K)
+    Kp, Np = _pad4(K), _pad4(N)
+    A = torch.randn(M, Kp, device="cuda", generator=g) * 0.7 + 0.3        # non-zero mean, as post-ReLU features
+    B = torch.randn((N, Kp) if tb else (K, Np), device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    A_lo, B_lo = _split(A), _split(B)
+    C = torch.full((M, Np), 3.0, device="cuda")
+    lib = _capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    nparts = lib.caae_gemm_tf32_stats_parts(M, N, K, Np) if stats else 0
+    assert (nparts > 0) == stats
+    parts = torch.zeros(max(nparts, 1) * 2 * N, dtype=torch.float64, device="cuda")
+    _capi.check(lib.caae_gemm_tf32x3(0, tb, M, N, K, A.data_ptr(), A_lo.data_ptr(), Kp, B.data_ptr(), B_lo.data_ptr(),
+                                     B.shape[1], C.data_ptr(), Np, bias.data_ptr(), 0, parts.data_ptr() if stats else None, st),
+                "caae_gemm_tf32x3")
+    torch.cuda.synchronize()
+    Ad = A[:, :K].double()
+    Bd = B[:, :K].double().T if tb else B[:, :N].double()
+    want = Ad @ Bd + bias.double()
+    scale = (Ad.abs() @ Bd.abs()).max()
+    err = (C[:, :N].double() - want).abs().max()
+    assert err <= 3e-6 * scale, (err.item(), scale.item())
+    if stats:
+        p = parts.view(nparts, 2, N).sum(0)
+        assert torch.allclose(p[0], C[:, :N].double().sum(0), rtol=1e-6, atol=1e-2)   # fp32 over 32 rows, fp64 across
+        assert torch.allclose(p[1], (C[:, :N].double() ** 2).sum(0), rtol=1e-6)

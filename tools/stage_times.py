@@ -100,7 +100,7 @@ def main():
                 (f"L{l + 1} proj gemm", lambda feat=feat, l=l, ci=ci, co=co: eng._gemm(0, 0, R, 2 * co, ci, feat, 320, eng.wf[l], 2 * co, eng.pq[l], 2 * co, eng.bf[l])),
                 (f"L{l + 1} edge_stats", lambda l=l, co=co: eng._c("caae_edge_stats", B, N, k, co, p(eng.pq[l]), 2 * co, p(eng.idx[l]), p(eng.parts))),
                 (f"L{l + 1} bn_finalize", lambda scope=scope, nparts=nparts: eng._bn_coeffs(scope, True, nparts, R * k, tr.decay)),
-                (f"L{l + 1} edge_apply", lambda l=l, co=co, bn=bn: eng._c("caae_edge_apply", B, N, k, co, p(eng.pq[l]), 2 * co, p(eng.idx[l]), p(bn["scale"]), p(bn["shift"]), p(eng.hcat[:, eng.offs[l]:]), 320)),
+                (f"L{l + 1} edge_apply", lambda l=l, co=co, bn=bn: eng._c("caae_edge_apply", B, N, k, co, p(eng.pq[l]), 2 * co, p(eng.idx[l]), p(bn["scale"]), p(bn["shift"]), p(eng.hcat[:, eng.offs[l]:]), 320, p(eng.hcat_lo[:, eng.offs[l]:]))),
                 (f"L{l + 1} edge_bwd_reduce", lambda args=args, d_out=d_out: eng._c("caae_edge_bwd_reduce", *args, p(d_out), 320, p(eng.parts))),
                 (f"L{l + 1} edge_bwd_apply", lambda args=args, d_out=d_out, bn=bn, l=l, co=co: eng._c("caae_edge_bwd_apply", *args, p(bn["coef"]), p(d_out), 320, p(eng.d_pq[l]), 2 * co)),
                 (f"L{l + 1} wgrad gemm", lambda feat=feat, l=l, ci=ci, co=co: eng._gemm(1, 0, ci, 2 * co, R, feat, 320, eng.d_pq[l], 2 * co, eng.d_wf[l], 2 * co)),
