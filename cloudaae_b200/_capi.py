@@ -47,6 +47,10 @@ _SIGNATURES = {
     "caae_gemm_tf32x3": "iiiiippippipipip" "p",
     "caae_split_tf32": "lipipi" "p",
     "caae_knn": "iiiipip" "p",
+    "caae_knn_ffma": "iiiipip" "p",
+    "caae_knn_classify": "iiipip" "p",
+    "caae_debug_knn_shortlist": "iiiipipp" "p",
+    "caae_knn_part": "ipiiiipip" "p",
     "caae_edge_stats": "iiiipipp" "p",
     "caae_edge_apply": "iiiipippppip" "p",
     "caae_edge_bwd_reduce": "iiiipippppppip" "p",

@@ -652,9 +652,14 @@ static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int
                              const float* coef, const float* dOut, int lddo, float* out, int ldo, double* parts,
                              cudaStream_t s, float* out_lo = nullptr) {
   const size_t smem = edge_cloud_smem(n, k, MODE);
-  if (smem > 48 * 1024) {
+  // the kernel also holds 33 KB of static shared memory: the opt-in is needed well below 48 KB of dynamic memory
+  // (a first call with n = 128 failed with "invalid argument" until a larger cloud had raised the limit).  Raised
+  // once per size class, not per call.
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(edge_cloud_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
   }
   edge_cloud_kernel<MODE><<<dim3(cout / ES_CH, b), dim3(32, 32), smem, s>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean,
                                                                           invstd, coef, dOut, lddo, out, ldo, parts, out_lo);

@@ -237,6 +237,8 @@ class _Engine:
         self.s_branch = [torch.cuda.Stream(**hi) for _ in range(2)] if self.concurrent else []
         self.s_wgrad = [torch.cuda.Stream(**hi) for _ in range(3)] if self.concurrent else []
         self.s_enc = torch.cuda.Stream(**hi) if self.concurrent else None
+        self.s_knn = torch.cuda.Stream(**hi) if self.concurrent else None
+        self.knn_flags = torch.zeros(batch, dtype=torch.int32, device=self.dev)
         self.d_emb_br = _take(3 * B, 1024).view(3, B, 1024)
         self._heads_pending = False
 
@@ -451,6 +453,8 @@ class _Engine:
                     self._split(self.v[f"{s_}/weights"], fout_, fin_, fout_, lo, fout_)
         if self.model == "dgcnn":
             feat, feat_lo, ldf, cknn = x, None, D, 3
+            # clouds padded with repeats of their visible points (identical rows stay identical in every layer)
+            self._c("caae_knn_classify", B, N, D, self._p(x), D, self._p(self.knn_flags))
             with self._on(se):   # the folded weights (and the low parts of the weights) depend on the parameters only
                 for l in range(4):
                     self._c("caae_edge_fold_weights", self.cins[l], self.couts[l], self._p(self.v[f"dgcnn{l + 1}/weights"]),
@@ -466,7 +470,14 @@ class _Engine:
                 with self._on(se):
                     self._gemm_fwd(R, 2 * co, ci, feat, feat_lo, ldf, self.wf[l], self.wf_lo[l], 2 * co, self.pq[l], 2 * co,
                                    self.bf[l])
-                self._c("caae_knn", B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
+                # heavily padded clouds (flagged once per forward, below) take the all-pairs kernel next to the
+                # tensor-core kernel of the others: disjoint halves of idx[l]
+                sk = self.s_knn
+                if sk is not None: self._fork(sk)
+                with self._on(sk):
+                    self._c("caae_knn_part", 2, self._p(self.knn_flags), B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
+                self._c("caae_knn_part", 1, self._p(self.knn_flags), B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
+                if sk is not None: self._join(sk)
                 if se is not None: self._join(se)
                 if train_enc:
                     self._c("caae_edge_stats", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),

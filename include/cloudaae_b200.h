@@ -124,6 +124,20 @@ int caae_split_tf32(long rows, int cols, const float* x, int ldx, float* lo, int
 /* pairwise_xyz_distance + knn (tf_util.py:597-632): x [b*n, ldx] (first c channels), idx i32[b*n,k],
  * k smallest of (|xi|^2 - 2 xi.xj) + |xj|^2, ascending, ties to the lower index, self included. */
 int caae_knn(int b, int n, int c, int k, const float* x, int ldx, int* idx, caae_stream_t stream);
+/* caae_knn screens the n x n distances on the tensor cores (split-precision Gram matrix in TMEM, n <= 256, c <= 64)
+ * and spends the exact fp32 arithmetic on a provably sufficient shortlist; caae_knn_ffma is the all-pairs FFMA kernel
+ * alone (the general path).  Both evaluate the distances on features centred on the cloud mean and return
+ * bit-identical indices. */
+int caae_knn_ffma(int b, int n, int c, int k, const float* x, int ldx, int* idx, caae_stream_t stream);
+/* Routing for batches that contain heavily padded clouds (convexHull()'s random repeats, hidden_point_removal.py:38-40):
+ * caae_knn_classify sets flags[cloud] = 1 when >= n/8 rows repeat an earlier row exactly; caae_knn_part(1, flags, ...)
+ * runs the tensor-core kernel on the unflagged clouds and caae_knn_part(2, flags, ...) the all-pairs kernel on the
+ * flagged ones — disjoint halves of the same result that may run on two streams. */
+int caae_knn_classify(int b, int n, int c, const float* x, int ldx, int* flags, caae_stream_t stream);
+int caae_debug_knn_shortlist(int b, int n, int c, int k, const float* x, int ldx, int* idx, int* counts,
+                             caae_stream_t stream); /* debug: per-row shortlist sizes of the tensor-core screen */
+int caae_knn_part(int part, const int* flags, int b, int n, int c, int k, const float* x, int ldx, int* idx,
+                  caae_stream_t stream);
 
 /* EdgeConv on the factorised projection PQ [b*n, >=2*cout] = [P | Q]: z_ij = P_i + Q_nn(i,j). */
 int caae_edge_parts(int b, int n, int k, int cout, int ldpq); /* fp64 partial rows caae_edge_stats / _bwd_reduce write */

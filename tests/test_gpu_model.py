@@ -169,6 +169,12 @@ def test_train_forward_losses_and_gradients(model, b, n, precision):
     # near-identical embeddings (random-init network) divides by a tiny batch std and amplifies the
     # 2e-4 TF32 perturbation of the embedding ~100x in the gradients behind it; 5e-2 bounds that.
     gtol = RTOL if precision == "fp32" else 5e-2
+    if b * n < 1024:
+        # 384 points: ONE ReLU decision on a pre-activation that is zero to within fp32 rounding moves 1/3840 of a
+        # channel's batch-norm backward statistics, i.e. every gradient element behind it, by ~1e-3 (observed 1.7e-3
+        # in 3 of 3072 elements for one seed, 4e-5 for the others — tools/debug_grad_b3.py; kNN agreement 1.0000 and
+        # features 5e-6 in the same run).  The benchmarked batch is asserted at 1e-3 in test_gpu_model_b128.py.
+        gtol = max(gtol, 2.5e-3)
     bad = {k: e for k, e in worst.items() if e > gtol}
     assert not bad, bad
 
@@ -287,3 +293,59 @@ def test_fused_gemm_statistics_equal_the_separate_statistics_pass():
     for k in bn1:
         assert torch.allclose(bn1[k], bn0[k], rtol=1e-4, atol=1e-6), k
     assert torch.allclose(l1, l0, rtol=1e-3, atol=1e-6), (l1, l0)
+
+
+def _knn_ffma(x, c, k):
+    b, n, ld = x.shape
+    idx = torch.empty(b, n, k, dtype=torch.int32, device="cuda")
+    _capi.check(_capi.lib().caae_knn_ffma(b, n, c, k, x.data_ptr(), ld, idx.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "knn_ffma")
+    return idx
+
+
+@pytest.mark.parametrize("b,n,c,ld,k", [(128, 256, 64, 320, 10), (128, 256, 3, 24, 10), (5, 200, 64, 64, 10), (3, 256, 24, 24, 16),
+                                        (2, 17, 8, 8, 10), (4, 256, 32, 32, 24)])
+@pytest.mark.parametrize("kind", ["features", "clustered", "duplicates", "padded3", "padded40"])
+def test_knn_tensor_core_screen_is_bit_identical_to_the_ffma_kernel(b, n, c, ld, k, kind):
+    """caae_knn (tcgen05 Gram-matrix screen + exact re-rank of a shortlist, knn_tc.cu) must return exactly the indices
+    of the all-pairs fp32 kernel: on post-ReLU-like features with a large common mean (the hard case for the error
+    bound: norms >> neighbour distances), on tight clusters, and with mass duplicates (shortlist overflow -> fix-up)."""
+    g = torch.Generator("cuda").manual_seed(n * 7 + c + k)
+    if kind == "features":
+        x = torch.relu(torch.randn(b, n, ld, device="cuda", generator=g) * 0.3 + 1.0)
+    elif kind == "clustered":
+        centers = torch.randn(b, 8, ld, device="cuda", generator=g)
+        x = centers[:, torch.arange(n, device="cuda") % 8] + 1e-3 * torch.randn(b, n, ld, device="cuda", generator=g)
+    elif kind == "duplicates":
+        x = torch.randn(b, n, ld, device="cuda", generator=g)
+        x[:, n // 3:] = x[:, :1]                        # two thirds of every cloud are copies of point 0
+    else:
+        # convexHull()'s padding (utils/hidden_point_removal.py:38-40): V visible points + random repeats of them
+        V = min(int(kind[6:]), n)
+        x = torch.randn(b, n, ld, device="cuda", generator=g)
+        pick = torch.randint(0, V, (b, n - V), device="cuda", generator=g)
+        x[:, V:] = torch.gather(x[:, :V], 1, pick[:, :, None].expand(-1, -1, ld))
+    got, want = _knn(x, c, k), _knn_ffma(x, c, k)
+    assert torch.equal(got, want)
+
+
+def test_knn_routing_of_padded_clouds_covers_the_batch_exactly():
+    """caae_knn_classify flags the clouds with >= n/8 repeated rows; caae_knn_part(1) + caae_knn_part(2) together must
+    equal the all-pairs kernel on every cloud, and each part must leave the other part's clouds untouched."""
+    b, n, c, k = 12, 256, 64, 10
+    g = torch.Generator("cuda").manual_seed(5)
+    x = torch.relu(torch.randn(b, n, c, device="cuda", generator=g) * 0.2 + 1.0)
+    for i, V in ((1, 3), (4, 40), (7, 100), (9, 230)):      # 253, 216, 156, 26 repeated rows
+        pick = torch.randint(0, V, (n - V,), device="cuda", generator=g)
+        x[i, V:] = x[i, pick]
+    lib, st = _capi.lib(), torch.cuda.current_stream().cuda_stream
+    flags = torch.full((b,), -7, dtype=torch.int32, device="cuda")
+    _capi.check(lib.caae_knn_classify(b, n, c, x.data_ptr(), c, flags.data_ptr(), st), "classify")
+    assert flags.tolist() == [0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0]   # 26 repeats < n/8 stay on the tensor-core path
+    want = _knn_ffma(x, c, k)
+    for part in (1, 2):
+        idx = torch.full((b, n, k), -1, dtype=torch.int32, device="cuda")
+        _capi.check(lib.caae_knn_part(part, flags.data_ptr(), b, n, c, k, x.data_ptr(), c, idx.data_ptr(), st), "part")
+        mine = (flags == (1 if part == 2 else 0))
+        assert torch.equal(idx[mine], want[mine])
+        assert (idx[~mine] == -1).all()

@@ -32,6 +32,21 @@ def main():
     syn = SegmentSynthesizer(load_models_xyz(device=dev), B, N, seed=1234)
     bt = {k: torch.from_numpy(v).to(dev) for k, v in bench.pose_batches(B, seed=0, pool=1)[0].items()}
     c, ax, tl = (bt[k] for k in bench.TRAIN_KEYS)
+    nmain = 9
+    tot = 0.0
+    for si, (name, ms, launches) in enumerate(measure(tr, syn, c, ax, tl, args.iters, args.detail)):
+        if name != "whole_step" and si < nmain:
+            tot += ms
+        print(f"{name:26s} {ms * 1000:9.1f} us   {launches:4d} C-ABI launches", flush=True)
+        if si == nmain - 1:
+            print(f"{'sum of stages':22s} {tot * 1000:9.1f} us")
+
+
+def measure(tr, syn, c, ax, tl, iters=30, detail=True):
+    """[(name, ms, C-ABI launches)] for the stages of one train step (first 9 entries) and, with detail, for single
+    kernels of the encoder — each captured as its own CUDA graph and replayed `iters` times (warm caches)."""
+    dev = tr.dev
+    B, N = tr.B, tr.N
     eng, p, M = tr.engine, _Engine._p, tr.M
     # one eager step so that every buffer holds sane values
     tr.train_step_online(syn, c, ax, tl)
@@ -96,8 +111,9 @@ def main():
                     p(bn["invstd"]))
             nparts = eng.lib.caae_edge_parts(B, N, k, co, 2 * co)
             out += [
-                (f"L{l + 1} knn", lambda feat=feat, l=l: eng._c("caae_knn", B, N, 64, k, p(feat), 320, p(eng.idx[l]))),
-                (f"L{l + 1} proj gemm", lambda feat=feat, l=l, ci=ci, co=co: eng._gemm(0, 0, R, 2 * co, ci, feat, 320, eng.wf[l], 2 * co, eng.pq[l], 2 * co, eng.bf[l])),
+                (f"L{l + 1} knn (tensor-core part)", lambda feat=feat, l=l: eng._c("caae_knn_part", 1, p(eng.knn_flags), B, N, 64, k, p(feat), 320, p(eng.idx[l]))),
+                (f"L{l + 1} knn (all-pairs part: padded clouds)", lambda feat=feat, l=l: eng._c("caae_knn_part", 2, p(eng.knn_flags), B, N, 64, k, p(feat), 320, p(eng.idx[l]))),
+                (f"L{l + 1} proj gemm", lambda feat=feat, l=l, ci=ci, co=co: eng._gemm_fwd(R, 2 * co, ci, feat, eng.hcat_lo[:, eng.offs[l - 1]:] if eng.x3 else None, 320, eng.wf[l], eng.wf_lo[l], 2 * co, eng.pq[l], 2 * co, eng.bf[l])),
                 (f"L{l + 1} edge_stats", lambda l=l, co=co: eng._c("caae_edge_stats", B, N, k, co, p(eng.pq[l]), 2 * co, p(eng.idx[l]), p(eng.parts))),
                 (f"L{l + 1} bn_finalize", lambda scope=scope, nparts=nparts: eng._bn_coeffs(scope, True, nparts, R * k, tr.decay)),
                 (f"L{l + 1} edge_apply", lambda l=l, co=co, bn=bn: eng._c("caae_edge_apply", B, N, k, co, p(eng.pq[l]), 2 * co, p(eng.idx[l]), p(bn["scale"]), p(bn["shift"]), p(eng.hcat[:, eng.offs[l]:]), 320, p(eng.hcat_lo[:, eng.offs[l]:]))),
@@ -109,24 +125,26 @@ def main():
         bn = eng.bn["dgcnn_agg"]
         W = tr.v["dgcnn_agg/weights"]
         out += [
-            ("L1 knn (xyz)", lambda: eng._c("caae_knn", B, N, 3, k, p(tr.x), eng.D, p(eng.idx[0]))),
-            ("agg gemm fwd", lambda: eng._gemm(0, 0, R, 1024, 320, eng.hcat, 320, W, 1024, eng.yagg, 1024, tr.v["dgcnn_agg/biases"])),
-            ("agg col_stats", lambda: eng._c("caae_col_stats", R, 1024, p(eng.yagg), 1024, p(eng.parts))),
+            ("L1 knn (xyz, tensor-core part)", lambda: eng._c("caae_knn_part", 1, p(eng.knn_flags), B, N, 3, k, p(tr.x), eng.D, p(eng.idx[0]))),
+            ("L1 knn (xyz, all-pairs part)", lambda: eng._c("caae_knn_part", 2, p(eng.knn_flags), B, N, 3, k, p(tr.x), eng.D, p(eng.idx[0]))),
+            ("knn classify", lambda: eng._c("caae_knn_classify", B, N, eng.D, p(tr.x), eng.D, p(eng.knn_flags))),
+            ("agg gemm fwd (+stats)", lambda: eng._dense_fwd("dgcnn_agg", eng.hcat, 320, R, True, tr.decay, eng.yagg, None, x_lo=eng.hcat_lo if eng.x3 else None)),
             ("agg bn_act_pool", lambda: eng._c("caae_bn_act_pool", B, N, 1024, p(eng.yagg), 1024, p(bn["scale"]), p(bn["shift"]), 0, p(eng.emb), None)),
             ("agg bn_bwd (3 launches)", lambda: eng._bn_bwd("dgcnn_agg", R, eng.yagg, eng.d_emb, 1024, N, 1.0 / N, None, eng.yagg)),
             ("agg wgrad gemm", lambda: eng._dense_wgrad("dgcnn_agg", eng.hcat, 320, R, eng.yagg, False)),
             ("agg dgrad gemm", lambda: eng._gemm(0, 1, R, 320, 1024, eng.yagg, 1024, W, 1024, eng.d_hcat, 320)),
             ("nn_distance fwd", lambda: tr._c("caae_nn_distance", B, M, p(tr.recon), M, p(tgt), p(tr.dist1), p(tr.idx1), p(tr.dist2), p(tr.idx2))),
+            ("nn_distance bwd", lambda: tr._c("caae_nn_distance_grad", B, M, p(tr.recon), M, p(tgt), p(tr.gconst), p(tr.idx1), p(tr.gconst), p(tr.idx2), p(tr.d_recon), p(tr.d_target))),
+            ("hpr_select (both problems)", lambda: syn._c("caae_hpr_select_pair", B, syn.nm + syn.no, p(syn.flip_all), syn.N, p(syn.pad_u), p(syn.visible), p(syn.num_vis), syn.nm, p(syn.flip_org), 4 * syn.N, p(syn.pad_u_org), p(syn.target), p(syn.num_vis_org), p(syn.points), syn.nm + syn.no)),
         ]
         return out
 
     stages = [("synthesis", st_synth), ("prepare_input", st_prepare), ("encoder_fwd", st_encoder_fwd),
               ("fc_fwd", st_fc_fwd), ("losses+chamfer_bwd", st_losses), ("fc_bwd", st_fc_bwd),
               ("encoder_bwd", st_encoder_bwd), ("adam", st_adam), ("whole_step", st_whole)]
-    nmain = len(stages)
-    if args.detail:
+    if detail:
         stages += detail_stages()
-    tot = 0.0
+    results = []
     for si, (name, fn) in enumerate(stages):
         s = torch.cuda.Stream(dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -144,16 +162,13 @@ def main():
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(args.iters):
+        for _ in range(iters):
             g.replay()
         b.record()
         torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / args.iters
-        if name != "whole_step" and si < nmain:
-            tot += ms
-        print(f"{name:26s} {ms * 1000:9.1f} us   {launches:4d} C-ABI launches", flush=True)
-        if si == nmain - 1:
-            print(f"{'sum of stages':22s} {tot * 1000:9.1f} us")
+        results.append((name, a.elapsed_time(b) / iters, launches))
+        del g
+    return results
 
 
 if __name__ == "__main__":
