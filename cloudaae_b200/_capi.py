@@ -87,6 +87,8 @@ _SIGNATURES = {
     "caae_radius_outlier": "iippidippp" "p",
     "caae_fps_seeded_f64": "iiipppppp" "p",
     "caae_icp_refine": "iiippippddiiddpppp" "p",
+    "caae_pose_transform_models": "iiipppppp" "p",
+    "caae_add_reduce": "iippppp" "p",
 }
 _SIGNATURES = {k: [_CODES[c] for c in v] for k, v in _SIGNATURES.items()}
 _SPECIAL = {

@@ -155,86 +155,123 @@ scatter_add_kernel(long total, int n, int m, const float* __restrict__ out_g, co
 }
 
 // ---- prob_sample: inclusive prefix sum + lower-bound search -------------------------------------
-// One CTA per row.  The prefix sum reproduces the reference's evaluation order for one 8192-element
-// chunk (4-element serial prefixes, an up/down sweep over the group totals) and its compensated
-// running sum across chunks (tf_sampling_g.cu:13-87), so cumulative values — and therefore the
-// searched indices — are bit-identical.
+// prob_sample(inp_p, inp_r) draws, per row, the first index whose cumulative probability reaches r * total
+// (reference tf_sampling_g.cu:7-104, tf_sampling.cpp:14-27,65-92).  The searched index depends on every rounding of
+// the cumulative sums, so the kernel reproduces the reference's SUMMATION TREE — not its code:
+//   * elements in groups of four with local prefixes x1, x1+x2, x3+(x1+x2), (x4+x3)+(x1+x2);
+//   * the group totals combined pairwise into aligned power-of-two blocks (block 2^(u+1) = left half + right half);
+//   * the inclusive prefix at group p = its aligned block of size lowbit(p+1) + the prefix in front of that block;
+//   * element = local prefix + prefix of the preceding groups, + the running sum of earlier 8192-element chunks,
+//     carried with the reference's two-term compensation.
+// Here the tree lives in registers: a thread owns four consecutive groups (tree levels 0-1), a warp 128 groups
+// (levels 2-6 by shuffles), the 16 warp totals go through one more shuffle tree (levels 7-10).  Groups past the end of
+// a chunk are zero (x + 0 = x exactly), which leaves every sum that exists in the reference unchanged.
 constexpr int kScanThreads = 512;
-constexpr int kScanChunk = 8192;
+constexpr int kScanChunk = 8192;     // elements per chunk = 2048 groups = 4 per thread
+
+__device__ __forceinline__ bool scan_down_target(int pos1, int w) {   // pos1 = position + 1 in units of 2^w-blocks' base level
+  return (pos1 & ((1 << w) - 1)) == 0 && ((pos1 >> w) & 1) && (pos1 >> w) >= 3;
+}
 
 __global__ void __launch_bounds__(kScanThreads)
 prob_sample_kernel(int n, int m, const float* __restrict__ inp_p, const float* __restrict__ inp_r,
                    float* __restrict__ temp, int* __restrict__ out) {
-  __shared__ float buffer4[kScanChunk];
-  __shared__ float buffer[kScanChunk / 4];
-  const int row = blockIdx.x, t = threadIdx.x;
+  __shared__ float warp_total[kScanThreads / 32], warp_prefix[kScanThreads / 32], chunk_total;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* __restrict__ src = inp_p + (size_t)row * n;
   float* __restrict__ cum = temp + (size_t)row * n;
-  float runningsum = 0.f, runningsum2 = 0.f;
-  for (int j = 0; j < n; j += kScanChunk) {
-    const int n24_i = min(n - j, kScanChunk);
-    const int n24 = (n24_i + 3) & ~3;
-    const int n2 = n24 >> 2;
-    for (int k = t * 4; k < n24_i; k += kScanThreads * 4) {
-      if (k + 3 < n24_i) {
-        float v1 = src[j + k], v2 = src[j + k + 1];
-        v2 = __fadd_rn(v2, v1);
-        float v3 = src[j + k + 2], v4 = src[j + k + 3];
-        v4 = __fadd_rn(v4, v3);
-        v3 = __fadd_rn(v3, v2);
-        v4 = __fadd_rn(v4, v2);
-        buffer4[k] = v1; buffer4[k + 1] = v2; buffer4[k + 2] = v3; buffer4[k + 3] = v4;
-        buffer[k >> 2] = v4;
-      } else {
+  float carry = 0.f, carry_lo = 0.f;                       // compensated running sum over chunks
+  for (int c0 = 0; c0 < n; c0 += kScanChunk) {
+    const int len = min(n - c0, kScanChunk);
+    const int last_group = ((len + 3) >> 2) - 1;
+    // ---- this thread's 16 elements: local prefixes loc[g][0..3] and group totals tot[g]
+    float loc[4][4], tot[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int e = (4 * tid + g) * 4;                     // first element of the group inside the chunk
+      if (e + 3 < len) {
+        const float x1 = src[c0 + e], x2 = src[c0 + e + 1], x3 = src[c0 + e + 2], x4 = src[c0 + e + 3];
+        const float s12 = __fadd_rn(x2, x1), s34 = __fadd_rn(x4, x3);
+        loc[g][0] = x1; loc[g][1] = s12; loc[g][2] = __fadd_rn(x3, s12); loc[g][3] = __fadd_rn(s34, s12);
+      } else {                                             // ragged tail group: a serial prefix, repeated to the group's end
         float v = 0.f;
-        for (int k2 = k; k2 < n24_i; ++k2) { v = __fadd_rn(v, src[j + k2]); buffer4[k2] = v; }
-        for (int k2 = n24_i; k2 < n24; ++k2) buffer4[k2] = v;
-        buffer[k >> 2] = v;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { if (e + i < len) v = __fadd_rn(v, src[c0 + e + i]); loc[g][i] = v; }
       }
+      tot[g] = loc[g][3];
     }
-    int u = 0;
-    for (; (2 << u) <= n2; ++u) {
-      __syncthreads();
-      for (int k = t; k < (n2 >> (u + 1)); k += kScanThreads) {
-        const int i1 = (((k << 1) + 2) << u) - 1, i2 = (((k << 1) + 1) << u) - 1;
-        buffer[i1] = __fadd_rn(buffer[i1], buffer[i2]);
-      }
+    // ---- up-sweep: levels 0-1 in the thread, 2-6 across the warp, 7-10 across the warp totals
+    float b1 = __fadd_rn(tot[1], tot[0]);
+    float b3 = __fadd_rn(__fadd_rn(tot[3], tot[2]), b1);
+    float T = b3;
+#pragma unroll
+    for (int w = 0; w < 5; ++w) {
+      const float t = __shfl_up_sync(0xffffffffu, T, 1 << w);
+      if (((lane + 1) & ((2 << w) - 1)) == 0) T = __fadd_rn(T, t);
     }
-    --u;
-    for (; u >= 0; --u) {
-      __syncthreads();
-      for (int k = t; k < ((n2 - (1 << u)) >> (u + 1)); k += kScanThreads) {
-        const int i1 = (((k << 1) + 3) << u) - 1, i2 = (((k << 1) + 2) << u) - 1;
-        buffer[i1] = __fadd_rn(buffer[i1], buffer[i2]);
+    if (lane == 31) warp_total[warp] = T;
+    __syncthreads();
+    if (warp == 0) {
+      float W = (lane < kScanThreads / 32) ? warp_total[lane] : 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float t = __shfl_up_sync(0xffffffffu, W, 1 << w);
+        if (((lane + 1) & ((2 << w) - 1)) == 0) W = __fadd_rn(W, t);
       }
+#pragma unroll
+      for (int w = 2; w >= 0; --w) {                       // down-sweep over the warp totals
+        const float t = __shfl_up_sync(0xffffffffu, W, 1 << w);
+        if (scan_down_target(lane + 1, w)) W = __fadd_rn(W, t);
+      }
+      if (lane < kScanThreads / 32) warp_prefix[lane] = W; // inclusive prefix at the end of each warp's 128 groups
     }
     __syncthreads();
-    for (int k = t * 4; k < n24; k += kScanThreads * 4) {
-      if (k != 0) {
-        const float add = buffer[(k >> 2) - 1];
-        buffer4[k] = __fadd_rn(buffer4[k], add);
-        buffer4[k + 1] = __fadd_rn(buffer4[k + 1], add);
-        buffer4[k + 2] = __fadd_rn(buffer4[k + 2], add);
-        buffer4[k + 3] = __fadd_rn(buffer4[k + 3], add);
-      }
+    // ---- down-sweep inside the warp (levels 6..2); a source one step in front of the warp is the previous warp's prefix
+    const float prev_warp = (warp > 0) ? warp_prefix[warp - 1] : 0.f;
+    if (lane == 31) T = warp_prefix[warp];
+    const int G1 = tid + 1;                                // this thread's position + 1 among the 512 thread blocks
+#pragma unroll
+    for (int w = 4; w >= 0; --w) {
+      const float t = __shfl_up_sync(0xffffffffu, T, 1 << w);
+      const float from = (lane + 1 == (1 << w)) ? prev_warp : t;
+      if (scan_down_target(G1, w)) T = __fadd_rn(T, from);
+    }
+    // ---- levels 1, 0 in the thread: P = inclusive prefix at the end of the previous thread's groups
+    float P = __shfl_up_sync(0xffffffffu, T, 1);
+    if (lane == 0) P = prev_warp;
+    float b0 = tot[0], b2 = tot[2];
+    if (tid > 0) { b1 = __fadd_rn(b1, P); b0 = __fadd_rn(b0, P); }
+    b2 = __fadd_rn(b2, b1);
+    // group prefixes in front of each of the four groups: P, b0, b1, b2; inclusive prefix of the last one: T
+    const float front[4] = {P, b0, b1, b2};
+    const float incl[4] = {b0, b1, b2, T};
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int grp = 4 * tid + g, e = grp * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (e + i < len) cum[c0 + e + i] = __fadd_rn(grp == 0 ? loc[g][i] : __fadd_rn(loc[g][i], front[g]), carry);
+      if (grp == last_group) chunk_total = incl[g];
     }
     __syncthreads();
-    for (int k = t; k < n24_i; k += kScanThreads) cum[j + k] = __fadd_rn(buffer4[k], runningsum);
-    const float tt = __fadd_rn(buffer[n2 - 1], runningsum2);
-    const float r2 = __fadd_rn(runningsum, tt);
-    runningsum2 = __fsub_rn(tt, __fsub_rn(r2, runningsum));
-    runningsum = r2;
+    const float tt = __fadd_rn(chunk_total, carry_lo);
+    const float next = __fadd_rn(carry, tt);
+    carry_lo = __fsub_rn(tt, __fsub_rn(next, carry));
+    carry = next;
     __syncthreads();
   }
-  // lower bound of q*total in the row's cumulative sums (binarysearchKernel, :90-104)
-  int base = 1;
-  while (base < n) base <<= 1;
+  // ---- the first index whose cumulative sum reaches q = r * total, probed in descending powers of two exactly as
+  // the reference probes it (so rows whose sums are not monotone to the last bit still agree)
+  int top = 1;
+  while (top < n) top <<= 1;
   const float total = cum[n - 1];
-  for (int jq = t; jq < m; jq += kScanThreads) {
+  for (int jq = tid; jq < m; jq += kScanThreads) {
     const float q = __fmul_rn(inp_r[(size_t)row * m + jq], total);
     int r = n - 1;
-    for (int k = base; k >= 1; k >>= 1)
-      if (r >= k && cum[r - k] >= q) r -= k;
+    for (int step = top; step > 0; step >>= 1) {
+      const int cand = r - step;
+      if (cand >= 0 && cum[cand] >= q) r = cand;
+    }
     out[(size_t)row * m + jq] = r;
   }
 }

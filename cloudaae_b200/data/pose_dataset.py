@@ -69,13 +69,40 @@ class PoseRecordDataset:
 
     def pinned_batches(self, batch_size: int, seed: int, epoch: int = 0, rank: int = 0, world: int = 1, depth: int = 2):
         """The same batches in a small ring of pinned host tensors (what `static.copy_(…, non_blocking=True)` of a
-        captured training step wants); a yielded batch is valid until `depth` more have been drawn."""
+        captured training step wants).
+
+        A slot is re-used `depth` batches later, and the host runs far ahead of the GPU (a step takes ~2 ms, refilling a
+        slot microseconds), so the consumer MUST tell the ring when its asynchronous host-to-device copy of a slot has
+        been enqueued: call ``batch["release"]()`` right after the ``copy_(..., non_blocking=True)`` calls, on the
+        stream that performs them.  It records a CUDA event; the slot is refilled only after that event has
+        completed.  A slot that was never released is refilled only after a full device synchronisation — slow, but
+        never torn (class_id of one batch with the pose of another)."""
         import torch
-        ring = [{"class_id": torch.empty(batch_size, dtype=torch.int32).pin_memory(),
-                 "axisangle": torch.empty(batch_size, 3).pin_memory(),
-                 "translation": torch.empty(batch_size, 3).pin_memory()} for _ in range(max(depth, 1))]
+        cuda = torch.cuda.is_available()
+        ring = [{"class_id": torch.empty(batch_size, dtype=torch.int32).pin_memory() if cuda else torch.empty(batch_size, dtype=torch.int32),
+                 "axisangle": torch.empty(batch_size, 3).pin_memory() if cuda else torch.empty(batch_size, 3),
+                 "translation": torch.empty(batch_size, 3).pin_memory() if cuda else torch.empty(batch_size, 3)}
+                for _ in range(max(depth, 1))]
+        state = [{"event": None, "handed_out": False} for _ in ring]
+
+        def make_release(st):
+            def release(stream=None):
+                if cuda:
+                    ev = torch.cuda.Event()
+                    ev.record(stream if stream is not None else torch.cuda.current_stream())
+                    st["event"] = ev
+                st["handed_out"] = False
+            return release
+
         for i, bt in enumerate(self.epoch(batch_size, seed, epoch, rank, world)):
-            slot = ring[i % len(ring)]
+            slot, st = ring[i % len(ring)], state[i % len(ring)]
+            if st["event"] is not None:
+                st["event"].synchronize()             # the copy that read this slot has finished
+                st["event"] = None
+            elif st["handed_out"] and cuda:
+                torch.cuda.synchronize()              # consumer never released the slot: be safe, not fast
             for k in KEYS:
                 slot[k].copy_(torch.from_numpy(bt[k]))
+            st["handed_out"] = True
+            slot["release"] = make_release(st)
             yield slot

@@ -221,7 +221,9 @@ def save_checkpoint(prefix: str, tensors: "dict[str, np.ndarray]") -> None:
     """Write `tensors` as a one-shard TensorBundle (``prefix.index`` + ``prefix.data-00000-of-00001``)."""
     data, items = bytearray(), []
     for name in sorted(tensors):
-        arr = np.ascontiguousarray(tensors[name])
+        arr = np.asarray(tensors[name])
+        if arr.ndim:                                   # (np.ascontiguousarray would turn a scalar into shape (1,))
+            arr = np.ascontiguousarray(arr)
         code = _DTYPE_CODES.get(arr.dtype)
         if code is None:
             raise TypeError(f"{name}: dtype {arr.dtype} has no TensorFlow code here")
@@ -307,16 +309,68 @@ def import_tf_checkpoint(variables, prefix: str, strict: bool = True) -> list[st
     return loaded
 
 
-def export_tf_checkpoint(variables, prefix: str, name_scope: str = "6d_pose") -> None:
+def export_tf_checkpoint(variables, prefix: str, name_scope: str = "6d_pose", global_step: float = 0.0,
+                         optimizer: dict | None = None) -> None:
     """Write `variables` under the reference's TensorFlow names and kernel shapes ([1,1,cin,cout] for the
-    encoder convolutions, [fan_in, cout] for the fully connected layers)."""
+    encoder convolutions, [fan_in, cout] for the fully connected layers).
+
+    A TF-1 ``tf.train.Saver()`` restores EVERY global variable of the graph it was built in, so the bundle also
+    carries what the reference's graphs hold besides the network: the float32 scalar ``Variable`` (the ``batch`` /
+    global-step variable of evaluate_cloudAAE_ycbv.py:411 and train_cloudAAE_ycbv.py:191) and, when `optimizer` =
+    {"adam_m": flat tensor, "adam_v": flat tensor, "t": steps taken} is given, the training graph's Adam state:
+    ``beta1_power``, ``beta2_power`` and the ``<var>/Adam`` / ``<var>/Adam_1`` slots (train…:259-262)."""
     mapping = tf_name_map(variables, name_scope)
     conv = {s for s, *_ in variables.layers if ("fc" not in s and "output" not in s)}
-    out = {}
-    for ours, tf_name in mapping.items():
-        arr = variables[ours].detach().cpu().numpy().astype(np.float32)
+
+    def shaped(ours, arr):
         scope = ours.split("/", 1)[0]
         if ours.endswith("/weights") and scope in conv:
-            arr = arr.reshape(1, 1, *arr.shape)
-        out[tf_name] = arr
+            return arr.reshape(1, 1, *arr.shape)
+        return arr
+
+    out = {}
+    for ours, tf_name in mapping.items():
+        out[tf_name] = shaped(ours, variables[ours].detach().cpu().numpy().astype(np.float32))
+    out["Variable"] = np.asarray(global_step, np.float32)
+    if optimizer is not None:
+        t = int(optimizer.get("t", 0))
+        out["beta1_power"] = np.asarray(0.9 ** (t + 1), np.float32)      # TF keeps beta^(t+1): initial value beta
+        out["beta2_power"] = np.asarray(0.999 ** (t + 1), np.float32)
+        for slot, key in (("Adam", "adam_m"), ("Adam_1", "adam_v")):
+            flat = optimizer[key].detach().cpu().numpy().astype(np.float32)
+            for ours in variables.trainable_names():
+                off, shape = variables.index[ours]
+                out[f"{mapping[ours]}/{slot}"] = shaped(ours, flat[off:off + int(np.prod(shape))].reshape(shape))
     save_checkpoint(prefix, out)
+
+
+def import_optimizer_state(variables, prefix: str):
+    """The other direction for a restart: global step and Adam slots of a TF-1 checkpoint, when it holds them.
+    Returns {"global_step": float | None, "t": int | None, "adam_m": flat tensor | None, "adam_v": ...} laid out like
+    ``variables.flat`` (load into CloudAAETrainer.load_state_dict)."""
+    import torch
+
+    _, entries = read_index(prefix + ".index")
+    mapping = tf_name_map(variables, available=entries)
+    want = {"Variable", "beta1_power", "beta2_power"} & set(entries)
+    slots = {}
+    for ours in variables.trainable_names():
+        for slot in ("Adam", "Adam_1"):
+            name = f"{mapping.get(ours, ours)}/{slot}"
+            if name in entries:
+                slots[name] = (ours, slot)
+    tensors = load_checkpoint(prefix, names=want | set(slots))
+    res = {"global_step": None, "t": None, "adam_m": None, "adam_v": None}
+    if "Variable" in tensors:
+        res["global_step"] = float(np.asarray(tensors["Variable"]).reshape(-1)[0])
+    if "beta1_power" in tensors:
+        b1p = float(np.asarray(tensors["beta1_power"]).reshape(-1)[0])
+        res["t"] = max(int(round(np.log(b1p) / np.log(0.9))) - 1, 0)
+    if slots:
+        m = torch.zeros_like(variables.flat, device="cpu"); v = torch.zeros_like(variables.flat, device="cpu")
+        for name, (ours, slot) in slots.items():
+            off, shape = variables.index[ours]
+            dst = m if slot == "Adam" else v
+            dst[off:off + int(np.prod(shape))] = torch.from_numpy(np.asarray(tensors[name], np.float32).reshape(-1))
+        res["adam_m"], res["adam_v"] = m, v
+    return res

@@ -264,3 +264,38 @@ def icp_refine(source: torch.Tensor, target: torch.Tensor, init: torch.Tensor, s
             float(radius_decay), int(outer), int(max_iteration), float(relative_fitness), float(relative_rmse),
             p(T), p(fit), p(rmse), p(iters), _stream(target)), "caae_icp_refine")
     return T, fit, rmse, iters
+
+
+# ---- ADD / ADD-S ------------------------------------------------------------------------------------------
+
+def add_metrics(source: torch.Tensor, T_gt: torch.Tensor, T_pred: torch.Tensor, source_of_seg=None):
+    """Pose errors of a batch of segments behind the prediction (evaluate…:571-575) or the ICP refinement
+    (:615-624): ADD = mean_x |(R x + t) - (R^ x + t^)| and ADD-S = mean_x min_y |(R x + t) - (R^ y + t^)| over the model
+    points x.  source f32[nsrc,ns,>=3] (the object models; `source_of_seg` i32[B] picks the model of each segment),
+    T_gt / T_pred f64[B,4,4].  Returns (add f64[B], add_s f64[B]) in the unit of the models (metres).  The nearest
+    neighbour search of ADD-S is the chamfer kernel (nn_distance)."""
+    if source.dim() != 3 or source.shape[2] < 3 or source.dtype != torch.float32:
+        raise InvalidArgumentError("add_metrics expects float32 source of shape (models, points, >=3)")
+    B = T_gt.shape[0]
+    for T in (T_gt, T_pred):
+        if T.shape != (B, 4, 4) or T.dtype != torch.float64:
+            raise InvalidArgumentError("add_metrics expects float64 poses of shape (batch, 4, 4)")
+    if source_of_seg is None and source.shape[0] != B:
+        raise InvalidArgumentError("add_metrics: without source_of_seg the source batch must equal the pose batch")
+    for t, name in ((source, "source"), (T_gt, "T_gt"), (T_pred, "T_pred")):
+        _capi.require_cuda(t, f"add_metrics({name})")
+    source, T_gt, T_pred = source.contiguous(), T_gt.contiguous(), T_pred.contiguous()
+    dev, n = source.device, source.shape[1]
+    sel = None if source_of_seg is None else _as_i32(source_of_seg, dev)
+    gt = torch.empty(B, n, 3, dtype=torch.float32, device=dev); pred = torch.empty_like(gt)
+    d1 = torch.empty(B, n, dtype=torch.float32, device=dev); d2 = torch.empty_like(d1)
+    i1 = torch.empty(B, n, dtype=torch.int32, device=dev); i2 = torch.empty_like(i1)
+    add = torch.empty(B, dtype=torch.float64, device=dev); adds = torch.empty_like(add)
+    p, lib = _capi.ptr, _capi.lib()
+    with torch.cuda.device(dev):
+        st = _stream(source)
+        _capi.check(lib.caae_pose_transform_models(B, n, source.shape[2], p(source), p(sel), p(T_gt), p(T_pred), p(gt),
+                                                   p(pred), st), "caae_pose_transform_models")
+        _capi.check(lib.caae_nn_distance(B, n, p(gt), n, p(pred), p(d1), p(i1), p(d2), p(i2), st), "caae_nn_distance")
+        _capi.check(lib.caae_add_reduce(B, n, p(gt), p(pred), p(d1), p(add), p(adds), st), "caae_add_reduce")
+    return add, adds

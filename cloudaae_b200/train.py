@@ -74,6 +74,27 @@ class CloudAAETrainer:
         if self.world > 1:
             broadcast_variables(self.v.flat, self.v.ema, group=process_group)
 
+    # ------------------------------------------------------------------ save / restore (train_cloudAAE_ycbv.py:423-430)
+    def state_dict(self):
+        """Everything a restart needs: parameters and moving averages, Adam moments, and the device-side step state
+        (step count, Adam t, bn_decay) — so bias correction and the bn_decay staircase continue where they stopped.
+        In data-parallel runs the batch-norm moving averages are per replica (the reference has one replica); save
+        rank 0's, or average them across ranks first (`average_ema`)."""
+        return {"variables": self.v.state_dict(), "adam_m": self.adam_m.detach().clone(), "adam_v": self.adam_v.detach().clone(),
+                "state": self.state.detach().clone()}
+
+    def load_state_dict(self, sd):
+        with torch.no_grad():
+            self.v.load_state_dict(sd["variables"])
+            self.adam_m.copy_(sd["adam_m"].to(self.dev)); self.adam_v.copy_(sd["adam_v"].to(self.dev))
+            self.state.copy_(sd["state"].to(self.dev))
+
+    def average_ema(self):
+        """Average the per-replica batch-norm moving averages across the process group (call before saving)."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.v.ema, group=self.pg)
+            self.v.ema.div_(self.world)
+
     # ------------------------------------------------------------------
     def _st(self):
         return torch.cuda.current_stream(self.dev).cuda_stream

@@ -291,6 +291,18 @@ int caae_icp_refine(int b, int ns, int src_stride, const float* source, const in
                     int max_iter, double rel_fitness, double rel_rmse, double* T_out, double* fitness,
                     double* inlier_rmse, int* iterations, caae_stream_t stream);
 
+/* ADD / ADD-S pose errors of a batch of segments (the pose is [rotmat | trans] of
+ * evaluate_cloudAAE_ycbv.py:571-575 or the ICP result of :615-624).  caae_pose_transform_models writes the model of
+ * every segment (models f32[nmodels,n,src_stride], class_of_seg i32[b] or NULL = segment index) under the ground-truth
+ * and the predicted pose (T f64[b,16] row-major 4x4) -> f32[b,n,3] each; the nearest-neighbour search of ADD-S is
+ * caae_nn_distance(gt, pred); caae_add_reduce returns add f64[b] = mean |gt_i - pred_i| and adds f64[b] =
+ * mean sqrt(dist_sq_i). */
+int caae_pose_transform_models(int b, int n, int src_stride, const float* models, const int* class_of_seg,
+                               const double* T_gt, const double* T_pred, float* out_gt, float* out_pred,
+                               caae_stream_t stream);
+int caae_add_reduce(int b, int n, const float* gt, const float* pred, const float* dist_sq, double* add, double* adds,
+                    caae_stream_t stream);
+
 /* Diagnostics (synchronous): copies the per-CTA phase timing of the LAST caae_hpr_select launch into
  * host_buf i64[512][8] = clock64 deltas {set-up, neighbourhood LPs, first verification, later rounds,
  * compaction + selection}, survivors, rounds, slots re-solved in round 0. */

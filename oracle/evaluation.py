@@ -183,3 +183,16 @@ def icp_refine(source, target, init, radius=0.01, radius_decay=0.9, outer=10, ma
 # synthetic YCB-Video-shaped frames (there is no real frame in the reference tree): the generator is a
 # data helper of the package, shared by the tests and bench.py
 from cloudaae_b200.data.synthetic_frames import render_frame  # noqa: E402,F401
+
+
+def add_metrics(model_xyz, T_gt, T_pred):
+    """ADD and ADD-S of one segment (Hinterstoisser et al. 2012; Xiang et al. 2018): model f32[n,3], poses f64[4,4].
+    Points are rounded to float32 after the transform, as the GPU path stores them; the nearest neighbour of ADD-S
+    by SciPy's KD-tree."""
+    from scipy.spatial import cKDTree
+    x = np.asarray(model_xyz, np.float32).astype(np.float64)
+    g = (x @ T_gt[:3, :3].T + T_gt[:3, 3]).astype(np.float32).astype(np.float64)
+    p = (x @ T_pred[:3, :3].T + T_pred[:3, 3]).astype(np.float32).astype(np.float64)
+    add = np.linalg.norm(g - p, axis=1).mean()
+    adds = cKDTree(p).query(g)[0].mean()
+    return add, adds

@@ -239,3 +239,37 @@ def test_front_end_and_icp_against_committed_golden_vectors():
     np.testing.assert_allclose(np_(T)[0], g["icp_T"], atol=1e-6)
     assert abs(float(fit[0]) - g["icp_stats"][0]) < 1e-3 and abs(float(rmse[0]) - g["icp_stats"][1]) < 1e-6
     assert abs(int(it[0]) - int(g["icp_stats"][2])) <= 2
+
+
+def test_add_and_add_s_metrics_match_oracle():
+    """ADD / ADD-S for a batch of segments of different classes: ground-truth pose vs a perturbed
+    prediction, vs the pose itself (both metrics 0) and vs a 180-degree flip of a near-symmetric object (ADD >> ADD-S)."""
+    models = cases.ycb_models()
+    t, a, c = cases.ycb_poses()
+    per = len(c) // 21
+    rng = np.random.default_rng(3)
+    classes = [0, 3, 7, 12, 20, 5]
+    Tg, Tp = [], []
+    for i, cls in enumerate(classes):
+        rec = cls * per + i
+        G = np.eye(4); G[:3, :3] = Rotation.from_rotvec(a[rec].astype(np.float64)).as_matrix(); G[:3, 3] = t[rec]
+        P = np.eye(4)
+        if i == 4:
+            P = G.copy()                                                   # perfect prediction
+        elif i == 5:
+            P[:3, :3] = G[:3, :3] @ Rotation.from_rotvec([0, 0, np.pi]).as_matrix(); P[:3, 3] = G[:3, 3]
+        else:
+            P[:3, :3] = Rotation.from_rotvec(rng.normal(0, 0.05, 3)).as_matrix() @ G[:3, :3]
+            P[:3, 3] = G[:3, 3] + rng.normal(0, 0.004, 3)
+        Tg.append(G); Tp.append(P)
+    src = torch.from_numpy(models).cuda()
+    add, adds = EV.add_metrics(src, torch.from_numpy(np.stack(Tg)).cuda(), torch.from_numpy(np.stack(Tp)).cuda(),
+                               source_of_seg=classes)
+    add, adds = add.cpu().numpy(), adds.cpu().numpy()
+    for i, cls in enumerate(classes):
+        wa, ws = E.add_metrics(models[cls], Tg[i], Tp[i])
+        assert abs(add[i] - wa) <= 1e-6 * max(wa, 1e-3), (i, add[i], wa)
+        assert abs(adds[i] - ws) <= 1e-5 * max(ws, 1e-3), (i, adds[i], ws)
+        assert adds[i] <= add[i] + 1e-9
+    assert add[4] == 0.0 and adds[4] == 0.0
+    assert add[5] > 2 * adds[5]

@@ -81,3 +81,36 @@ def test_pinned_ring_yields_the_same_batches():
             break
         assert bt["translation"].is_pinned() and (bt["translation"].numpy() == want[i]["translation"]).all()
         assert (bt["class_id"].numpy() == want[i]["class_id"]).all()
+
+
+
+def test_pinned_ring_never_refills_a_slot_before_its_release_event():
+    """The ring re-uses a slot `depth` batches later; it must wait for the consumer's release event (recorded after the
+    asynchronous host-to-device copy) — and fall back to a full synchronisation when a slot was never released."""
+    import torch
+    ds = _ds()
+    want = list(ds.epoch(16, seed=3))[:6]
+    waited = []
+
+    class FakeEvent:
+        def __init__(self, tag): self.tag = tag
+        def synchronize(self): waited.append(self.tag)
+
+    it = ds.pinned_batches(16, seed=3, depth=2)
+    for i in range(6):
+        bt = next(it)
+        assert callable(bt["release"])
+        assert (bt["class_id"].numpy() == want[i]["class_id"]).all() and (bt["axisangle"].numpy() == want[i]["axisangle"]).all()
+        bt["release"]()                      # CPU build: no event; the slot is simply handed back
+    if torch.cuda.is_available():
+        it = ds.pinned_batches(16, seed=3, depth=2)
+        seen = []
+        for i in range(5):
+            bt = next(it)
+            dev = {k: bt[k].cuda(non_blocking=True) for k in ("class_id", "axisangle", "translation")}
+            bt["release"]()
+            seen.append(dev)
+        torch.cuda.synchronize()
+        for i, dev in enumerate(seen):       # no torn or overwritten batch
+            assert (dev["class_id"].cpu().numpy() == want[i]["class_id"]).all()
+            assert (dev["translation"].cpu().numpy() == want[i]["translation"]).all()

@@ -79,3 +79,24 @@ def test_corrupt_files_are_rejected(tmp_path):
     with pytest.raises(T.CheckpointFormatError, match="crc32c"):
         T.load_checkpoint(prefix, verify_crc=True)
     assert T.masked_crc32c(b"123456789") == ((((0xE3069283 >> 15) | (0xE3069283 << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def test_exported_bundle_holds_everything_a_tf1_saver_restores(tmp_path):
+    """tf.train.Saver() restores every global variable of its graph: the evaluation graph needs the float32 scalar
+    'Variable' (evaluate_cloudAAE_ycbv.py:411), the training graph also beta1_power / beta2_power and the Adam slots —
+    the exported key set must cover the reference snapshot's own index."""
+    v = Variables(dgcnn_layers(256, 24), device="cpu", seed=2)
+    m = torch.rand_like(v.flat); vv = torch.rand_like(v.flat)
+    prefix = str(tmp_path / "model.ckpt")
+    T.export_tf_checkpoint(v, prefix, global_step=1234.0, optimizer={"adam_m": m, "adam_v": vv, "t": 7})
+    _, ours = T.read_index(prefix + ".index")
+    _, ref = T.read_index(GOLDEN)
+    assert set(ref) <= set(ours), sorted(set(ref) - set(ours))[:5]
+    for name in ref:                                             # same shapes and dtypes as TensorFlow wrote them
+        assert ours[name]["shape"] == ref[name]["shape"] and ours[name]["dtype"] == ref[name]["dtype"], name
+    st = T.import_optimizer_state(Variables(dgcnn_layers(256, 24), device="cpu", seed=3), prefix)
+    assert st["global_step"] == 1234.0 and st["t"] == 7
+    for name in ("dgcnn_agg/weights", "dgcnn_output/biases", "dgcnn1/bn/gamma"):
+        off, shape = v.index[name]
+        k = int(np.prod(shape))
+        assert torch.equal(st["adam_m"][off:off + k], m[off:off + k]) and torch.equal(st["adam_v"][off:off + k], vv[off:off + k])
