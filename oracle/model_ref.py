@@ -7,8 +7,12 @@ carry (tests use float64 on CPU for a tight bound, float32 for "what TF computes
                    :597-618 (pairwise_xyz_distance), :621-632 (knn), :635-669 (get_edge_feature)
   losses/chamfer_loss.py, losses/trans_distance.py, losses/angular_distance_taylor.py
   train_cloudAAE_ycbv.py:196-273 (bn_decay schedule, input prep, total loss, Adam)
-Parity unpinned by reference tests (the reference has none, and TensorFlow 1.12 is not installable
-here); autograd on this restatement defines the expected gradients.
+PINNED against the reference's own code: oracle/ref_py executes /root/reference/models/pointnet_ycb_23_decoder_4.py,
+utils/tf_util.py and losses/*.py in place (eager TensorFlow stand-in over torch) and
+tests/test_ref_py_pins_model_oracle.py requires this file to reproduce their outputs, losses, moving-average updates
+and the gradient of every trainable variable to 1e-10 — plus the vectors that run committed under
+tests/golden/ref_py_golden.npz for boxes without /root/reference.  (TensorFlow 1.12 itself is not installable here, so
+the arithmetic of TF's kernels is represented by float64 torch ops.)
 """
 from __future__ import annotations
 

@@ -3,8 +3,10 @@
 Follows train_cloudAAE_ycbv.py:57-117, 206-226, utils/hidden_point_removal.py:6-73,
 utils/generate_occluder.py:38-81, utils/sample_pose_in_frustum.py:42-70 and
 losses/angular_distance_taylor.py:6-66.  TensorFlow's RNG cannot be reproduced, so every random
-draw is an explicit argument (SURVEY.md §7 hard part 7).  Parity unpinned by reference tests
-(there are none); `scipy.spatial.ConvexHull` is the very call the reference makes.
+draw is an explicit argument (SURVEY.md §7 hard part 7).  PINNED against the reference's own utilities executed in
+place (oracle/ref_py; tests/test_ref_py_pins_synthesis_oracle.py: occluder bit-exact, flips to a few fp32 ulps, visible
+sets identical through the same scipy.spatial.ConvexHull call) and against the vectors committed from that run
+(tests/golden/ref_py_synth_golden.npz).  SciPy's version is the one thing the reference does not pin.
 """
 from __future__ import annotations
 
