@@ -46,6 +46,7 @@ _SIGNATURES = {
     "caae_gemm_tf32_stats": "iiipipipipp" "p",
     "caae_gemm_tf32x3": "iiiiippippipipip" "p",
     "caae_split_tf32": "lipipi" "p",
+    "caae_gemm_tf32_pool": "iiippippipppiipp" "p",
     "caae_knn": "iiiipip" "p",
     "caae_knn_ffma": "iiiipip" "p",
     "caae_knn_classify": "iiipip" "p",

@@ -57,6 +57,13 @@ struct GemmParams {
   double* stats_parts;  // persistent kernel: per (row tile, lane quadrant) column sums / sums of squares of C (or NULL)
   int tma_store;    // 128 x 128 kernel: 1 = write C with TMA bulk stores from a swizzled staging box (map_c valid),
                     // 2 = C += tile with TMA bulk reductions (accumulate without split-K)
+  // pooled epilogue (inference: batch norm is affine, so bias + BN + ReLU + mean / max over a cloud's points end in the
+  // GEMM and the [M, N] activation is never stored): pool_mode 1 = sum, 2 = max of relu(v * pool_scale[c] + pool_shift[c])
+  // over each (256-row tile, lane quadrant) -> pool_parts f32[tiles_m * 4][N]; 0 = off
+  int pool_mode;
+  const float* pool_scale;
+  const float* pool_shift;
+  float* pool_parts;
   int x3;           // split-precision ("3xTF32") product: C = A*B + A_lo*B + A*B_lo with A_lo = A - tf32(A), B_lo likewise
                     // (map_a_lo / map_b_lo valid) — fp32-grade accuracy at three tensor-core passes
 };
@@ -607,8 +614,40 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         if (X3) return p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
         return *reinterpret_cast<const float4*>(s_bias + col);
       };
+      float pool_acc[2] = {p.pool_mode == 2 ? -INFINITY : 0.f, p.pool_mode == 2 ? -INFINITY : 0.f};
       auto store_item = [&](uint32_t (&r)[32], int w) {
         const int h = w / NC, c0 = (w % NC) * 32;
+        if (p.pool_mode != 0) {
+          // inference epilogue: nothing is stored.  relu(bn(v)) goes through the warp's staging box so that lane l can
+          // reduce column l over the 32 rows (the statistics path's access pattern: 32 distinct banks per row)
+          const uint32_t box = stg + (uint32_t)(warp - 2) * Cfg::STG_WARP;
+          const uint32_t rowaddr = box + (uint32_t)lane * 128u;
+          __syncwarp();                                     // the previous item's column reads are done
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = bias4(n0 + c0 + j);
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pool_scale + n0 + c0 + j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pool_shift + n0 + c0 + j));
+            float4 v;
+            v.x = fmaxf(fmaf(__uint_as_float(r[j]) + bv.x, sc.x, sh.x), 0.f);
+            v.y = fmaxf(fmaf(__uint_as_float(r[j + 1]) + bv.y, sc.y, sh.y), 0.f);
+            v.z = fmaxf(fmaf(__uint_as_float(r[j + 2]) + bv.z, sc.z, sh.z), 0.f);
+            v.w = fmaxf(fmaf(__uint_as_float(r[j + 3]) + bv.w, sc.w, sh.w), 0.f);
+            st_shared_v4(rowaddr + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4), v);
+          }
+          __syncwarp();
+          const int rmax = min(32, p.M - (m0 + h * TBM + quad * 32));
+          const uint32_t col = box + (uint32_t)((lane & 3) << 2);
+          float red = p.pool_mode == 2 ? -INFINITY : 0.f;
+          for (int rr = 0; rr < rmax; ++rr) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(col + (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7))) << 4)));
+            red = p.pool_mode == 2 ? fmaxf(red, v) : red + v;
+          }
+          const int slot = ((w - part) >> 1) & 1;
+          pool_acc[slot] = p.pool_mode == 2 ? fmaxf(pool_acc[slot], red) : pool_acc[slot] + red;
+          return;
+        }
         if (!p.accumulate) {
           // registers -> swizzled shared-memory box -> one TMA store of 32 rows x 128 bytes (full lines; rows past M
           // are clipped by the tensor map).  A thread-per-row STG.128 writes 16 bytes to 32 different lines per
@@ -680,7 +719,12 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-      if (p.stats_parts != nullptr && !p.accumulate) {
+      if (p.pool_mode != 0) {
+        float* prow = p.pool_parts + (size_t)((id / tiles_n) * 4 + quad) * p.N;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) prow[n0 + (part + 2 * sl) * 32 + lane] = pool_acc[sl];
+      }
+      if (p.stats_parts != nullptr && !p.accumulate && p.pool_mode == 0) {
         // one partial row per (row tile, lane quadrant): the layout caae_bn_finalize reduces ([row][2][N])
         double* prow = p.stats_parts + (size_t)((id / tiles_n) * 4 + quad) * 2 * p.N;
 #pragma unroll
@@ -780,12 +824,15 @@ extern "C" int caae_gemm_tf32_supported(int transa, int transb, int M, int N, in
   return 1;
 }
 
+struct PoolEpilogue { int mode; const float* scale; const float* shift; float* parts; };
+
 static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B,
                           int ldb, float* C, int ldc, const float* bias, int accumulate, double* stats_parts,
-                          caae_stream_t stream, const float* A_lo = nullptr, const float* B_lo = nullptr) {
+                          caae_stream_t stream, const float* A_lo = nullptr, const float* B_lo = nullptr,
+                          const PoolEpilogue* pool = nullptr) {
   CAAE_RETURN_IF(M < 0 || N < 0 || K < 0, CAAE_E_BADSHAPE);
   if (M == 0 || N == 0) return CAAE_OK;
-  CAAE_RETURN_IF(!C || !A || !B, CAAE_E_NULLPTR);
+  CAAE_RETURN_IF((!C && !pool) || !A || !B, CAAE_E_NULLPTR);
   CAAE_RETURN_IF(ldc < N || lda < (transa ? M : K) || ldb < (transb ? K : N), CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!caae_gemm_tf32_supported(transa, transb, M, N, K, A, lda, B, ldb), CAAE_E_UNSUPPORTED);
   const bool x3 = A_lo != nullptr || B_lo != nullptr;
@@ -814,6 +861,8 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
   }
 
   GemmParams p;
+  p.pool_mode = pool ? pool->mode : 0;
+  p.pool_scale = pool ? pool->scale : nullptr; p.pool_shift = pool ? pool->shift : nullptr; p.pool_parts = pool ? pool->parts : nullptr;
   p.x3 = x3 ? 1 : 0;
   p.tma_store = 0;
   p.stats_parts = nullptr;
@@ -829,10 +878,11 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
   // tall / wide / short-K forward contractions: persistent 256 x 128 tiles with the epilogue overlapped
   static const bool persist_enabled = [] { const char* e = getenv("CAAE_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
   const bool persist_ok = persist_enabled && !transa && N % TBN == 0 && N <= PS_MAXN && N >= 512 &&
-                          M >= 256 * kNumSMs / 2 && num_kb >= 2 && num_kb <= 16 && ldc % 4 == 0 &&
+                          (M >= 256 * kNumSMs / 2 || pool != nullptr) && num_kb >= 2 && num_kb <= 16 && ldc % 4 == 0 &&
                           (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
                           (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 3) == 0);
   if (stats_parts != nullptr && (!persist_ok || accumulate)) return CAAE_E_UNSUPPORTED;
+  if (pool != nullptr && (!persist_ok || accumulate || N % 4 != 0)) return CAAE_E_UNSUPPORTED;
   p.stats_parts = stats_parts;
   if (persist_ok) {
     CUtensorMap map_a2, map_b2;
@@ -851,9 +901,11 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
       if (e != cudaSuccess) return (int)e;
       psattr = true;
     }
-    CUtensorMap map_c2;
-    rc = make_map_c(&map_c2, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc);
-    if (rc) return rc;
+    CUtensorMap map_c2 = map_a2;   // (unused by the pooled epilogue)
+    if (pool == nullptr) {
+      rc = make_map_c(&map_c2, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc);
+      if (rc) return rc;
+    }
     const int tm = (M + 2 * TBM - 1) / (2 * TBM), tn = N / TBN;
     p.kb_per_split = num_kb; p.atomic = 0; p.accumulate = accumulate;
     const int ctas = tm * tn < kNumSMs ? tm * tn : kNumSMs;
@@ -980,6 +1032,39 @@ extern "C" int caae_split_tf32(long rows, int cols, const float* x, int ldx, flo
   long blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   split_tf32_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(rows, cols, x, ldx, lo, ldlo);
+  return CAAE_LAUNCH_STATUS();
+}
+
+// Inference epilogue of the last encoder convolution (models/pointnet_ycb_23_decoder_4.py:410-426 dgcnn_agg -> mean over
+// the points; :55-60 pn_conv5 -> max): with moving-average batch norm the layer is affine (utils/tf_util.py:507-510), so
+// pooled[g][c] = mean / max over the `group` = 256 rows of cloud g of relu((A B + bias)[r][c] * scale[c] + shift[c]) comes
+// straight out of the GEMM epilogue and the [M, N] activation (134 MB at B = 128) is never written.  mode 1 = mean,
+// 2 = max.  parts f32[ceil(M / 256) * 4][N] is scratch.  Split-precision product when A_lo / B_lo are given.
+__global__ void pool_finalize_kernel(int groups, int N, const float* __restrict__ parts, int mode, float inv_group,
+                                     float* __restrict__ pooled) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)groups * N; e += (long)gridDim.x * blockDim.x) {
+    const long g = e / N;
+    const int c = (int)(e - g * N);
+    const float a = parts[(g * 4 + 0) * N + c], b = parts[(g * 4 + 1) * N + c], c2 = parts[(g * 4 + 2) * N + c],
+                d = parts[(g * 4 + 3) * N + c];
+    pooled[e] = mode == 2 ? fmaxf(fmaxf(a, b), fmaxf(c2, d)) : ((a + b) + (c2 + d)) * inv_group;
+  }
+}
+
+extern "C" int caae_gemm_tf32_pool(int M, int N, int K, const float* A, const float* A_lo, int lda, const float* B,
+                                   const float* B_lo, int ldb, const float* bias, const float* scale, const float* shift,
+                                   int mode, int group, float* parts, float* pooled, caae_stream_t stream) {
+  CAAE_RETURN_IF(mode != 1 && mode != 2, CAAE_E_BADSHAPE);
+  CAAE_RETURN_IF(group != 2 * TBM || M % group != 0, CAAE_E_UNSUPPORTED);   // one 256-row tile = one cloud
+  CAAE_RETURN_IF(!scale || !shift || !parts || !pooled, CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) != 0 ||
+                 (bias && (reinterpret_cast<uintptr_t>(bias) & 15)), CAAE_E_UNSUPPORTED);
+  PoolEpilogue pe{mode, scale, shift, parts};
+  // (C is not written: the address only has to satisfy the alignment checks of the shared code path)
+  const int rc = gemm_tf32_impl(0, 0, M, N, K, A, lda, B, ldb, parts, N, bias, 0, nullptr, stream, A_lo, B_lo, &pe);
+  if (rc) return rc;
+  const long total = (long)(M / group) * N;
+  pool_finalize_kernel<<<(int)((total + 255) / 256), 256, 0, as_stream(stream)>>>(M / group, N, parts, mode, 1.f / (float)group, pooled);
   return CAAE_LAUNCH_STATUS();
 }
 

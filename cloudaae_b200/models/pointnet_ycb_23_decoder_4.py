@@ -239,6 +239,7 @@ class _Engine:
         self.s_enc = torch.cuda.Stream(**hi) if self.concurrent else None
         self.s_knn = torch.cuda.Stream(**hi) if self.concurrent else None
         self.knn_flags = torch.zeros(batch, dtype=torch.int32, device=self.dev)
+        self.pool_parts = torch.empty(4 * batch * 1024, dtype=torch.float32, device=self.dev)   # pooled-epilogue scratch
         self.d_emb_br = _take(3 * B, 1024).view(3, B, 1024)
         self._heads_pending = False
 
@@ -380,6 +381,25 @@ class _Engine:
                     self._p(v[f"{scope}/bn/ema_mean"]), self._p(v[f"{scope}/bn/ema_var"]), self._p(bn["scale"]),
                     self._p(bn["shift"]))
 
+    def _pooled_fwd(self, scope, x, x_lo, ldx, training, want_activation, mode):
+        """Inference form of the last encoder convolution: moving-average batch norm is affine, so bias + BN + ReLU + the
+        mean (mode 1) / max (mode 2) over a cloud's points are reduced in the GEMM epilogue and the [B*N, 1024]
+        activation is never stored (caae_gemm_tf32_pool).  False when the configuration needs the stored activation
+        (training statistics, end_points['layer_before_embedding'], num_point != 256, FFMA precision)."""
+        fin, fout, _ = self.scopes[scope]
+        W = self.v[f"{scope}/weights"]
+        if (training or want_activation or self.N != 256 or self.precision != "tf32" or self.R * fin * fout < (1 << 28) or
+                os.environ.get("CLOUDAAE_POOL_EPILOGUE", "1") == "0" or
+                not self.lib.caae_gemm_tf32_supported(0, 0, self.R, fout, fin, self._p(x), ldx, self._p(W), fout)):
+            return False
+        bn = self.bn[scope]
+        self._bn_coeffs(scope, False, 1, self.R, None)
+        w_lo = self.w_lo.get(scope) if (self.x3 and x_lo is not None) else None
+        self._c("caae_gemm_tf32_pool", self.R, fout, fin, self._p(x), self._p(x_lo if w_lo is not None else None), ldx, self._p(W),
+                self._p(w_lo), fout, self._p(self.v[f"{scope}/biases"]), self._p(bn["scale"]), self._p(bn["shift"]), mode, self.N,
+                self._p(self.pool_parts), self._p(self.emb))
+        return True
+
     def _dense_fwd(self, scope, x, ldx, R, training, decay, y, a, x_lo=None):
         """y = x W + b; (BN + ReLU -> a) when the layer has BN (tf_util.conv2d 1x1 / fully_connected)."""
         fin, fout, has_bn = self.scopes[scope]
@@ -490,25 +510,35 @@ class _Engine:
                         self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320, self._p(feat_lo))
                 feat, ldf, cknn = out, 320, co
             scope = "dgcnn_agg"
-            self._dense_fwd(scope, self.hcat, 320, R, train_enc, decay, self.yagg, None,
-                            x_lo=self.hcat_lo if self.x3 else None)
             bn = self.bn[scope]
-            self._c("caae_bn_act_pool", B, N, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]),
-                    self._p(bn["shift"]), 0, self._p(self.emb), None)
+            if not self._pooled_fwd(scope, self.hcat, self.hcat_lo if self.x3 else None, 320, train_enc, want_before_embedding, 1):
+                self._dense_fwd(scope, self.hcat, 320, R, train_enc, decay, self.yagg, None,
+                                x_lo=self.hcat_lo if self.x3 else None)
+                self._c("caae_bn_act_pool", B, N, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]),
+                        self._p(bn["shift"]), 0, self._p(self.emb), None)
             if want_before_embedding:
                 before = torch.empty(R, 1024, dtype=torch.float32, device=self.dev)
                 self._c("caae_bn_act", R, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]), self._p(bn["shift"]),
                         1, self._p(before), 1024)
         else:
             inp, ldi = x, D
+            pooled = False
             for i, scope in enumerate(self.enc):
                 last = i == len(self.enc) - 1
+                if last and not train_enc and self.x3 and scope in self.w_lo:
+                    if scope not in self.a_lo:
+                        self.a_lo[scope] = torch.empty(R, ldi, dtype=torch.float32, device=self.dev)
+                    self._split(inp, ldi, R, ldi, self.a_lo[scope], ldi)
+                    pooled = self._pooled_fwd(scope, inp, self.a_lo[scope], ldi, train_enc, False, 2)
+                if pooled:
+                    break
                 self._dense_fwd(scope, inp, ldi, R, train_enc, decay, self.enc_y[i], None if last else self.enc_a[i])
                 if not last:
                     inp, ldi = self.enc_a[i], self.scopes[scope][1]
-            bn = self.bn[self.enc[-1]]
-            self._c("caae_bn_act_pool", B, N, 1024, self._p(self.enc_y[-1]), 1024, self._p(bn["scale"]),
-                    self._p(bn["shift"]), 1, self._p(self.emb), self._p(self.argmax))
+            if not pooled:
+                bn = self.bn[self.enc[-1]]
+                self._c("caae_bn_act_pool", B, N, 1024, self._p(self.enc_y[-1]), 1024, self._p(bn["scale"]),
+                        self._p(bn["shift"]), 1, self._p(self.emb), self._p(self.argmax))
         if se is not None: self._join(se)
         self.forward_fc(train_fc, decay)
         outs = [self.fc_y[br[-1]] for br in self.branches]

@@ -118,6 +118,14 @@ int caae_gemm_tf32_supported(int transa, int transb, int M, int N, int K, const 
 int caae_gemm_tf32x3(int transa, int transb, int M, int N, int K, const float* A, const float* A_lo, int lda,
                      const float* B, const float* B_lo, int ldb, float* C, int ldc, const float* bias, int accumulate,
                      double* parts, caae_stream_t stream);
+/* Inference epilogue of the last encoder convolution (dgcnn_agg -> mean over the points, models/...:410-426; pn_conv5 ->
+ * max, :55-60).  With moving-average batch norm the layer is affine (utils/tf_util.py:507-510), so
+ * pooled[g][c] = mean (mode 1) / max (mode 2) over the group = 256 rows of cloud g of relu((A B + bias) * scale + shift)
+ * is reduced in the GEMM epilogue and the [M, N] activation is never stored.  A_lo / B_lo NULL: single TF32 pass.
+ * parts f32[M / 256 * 4][N] scratch, pooled f32[M / 256][N]. */
+int caae_gemm_tf32_pool(int M, int N, int K, const float* A, const float* A_lo, int lda, const float* B, const float* B_lo,
+                        int ldb, const float* bias, const float* scale, const float* shift, int mode, int group,
+                        float* parts, float* pooled, caae_stream_t stream);
 /* lo[r][c] = x[r][c] - tf32_round_to_nearest_even(x[r][c])  (exact in fp32) */
 int caae_split_tf32(long rows, int cols, const float* x, int ldx, float* lo, int ldlo, caae_stream_t stream);
 

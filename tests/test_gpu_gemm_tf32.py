@@ -240,3 +240,28 @@ def test_gemm_tf32x3_is_fp32_grade(M, N, K, tb, stats):
         p = parts.view(nparts, 2, N).sum(0)
         assert torch.allclose(p[0], C[:, :N].double().sum(0), rtol=1e-6, atol=1e-2)   # fp32 over 32 rows, fp64 across
         assert torch.allclose(p[1], (C[:, :N].double() ** 2).sum(0), rtol=1e-6)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("B,N,K,x3", [(128, 1024, 320, True), (8, 1024, 320, True), (3, 512, 128, False), (128, 1024, 128, True)])
+def test_gemm_pool_epilogue_equals_bn_relu_pool_of_the_full_product(B, N, K, x3, mode):
+    """caae_gemm_tf32_pool: mean / max over each cloud's 256 rows of relu((A W + bias) * scale + shift), reduced in the GEMM
+    epilogue without storing the activation, vs the float64 computation (evaluate-mode dgcnn_agg / pn_conv5)."""
+    M = B * 256
+    g = torch.Generator("cuda").manual_seed(B + N + K + mode)
+    A = torch.randn(M, K, device="cuda", generator=g) * 0.5 + 0.2
+    W = torch.randn(K, N, device="cuda", generator=g) * 0.1
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    scale = torch.rand(N, device="cuda", generator=g) + 0.5
+    shift = torch.randn(N, device="cuda", generator=g) * 0.3
+    A_lo, W_lo = (_split(A), _split(W)) if x3 else (None, None)
+    parts = torch.empty(4 * B * N, device="cuda")
+    pooled = torch.full((B, N), 7.0, device="cuda")
+    p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    _capi.check(_capi.lib().caae_gemm_tf32_pool(M, N, K, p(A), p(A_lo), K, p(W), p(W_lo), N, p(bias), p(scale), p(shift), mode, 256,
+                                                p(parts), p(pooled), torch.cuda.current_stream().cuda_stream), "caae_gemm_tf32_pool")
+    torch.cuda.synchronize()
+    y = torch.relu((A.double() @ W.double() + bias.double()) * scale.double() + shift.double()).view(B, 256, N)
+    want = y.mean(1) if mode == 1 else y.max(1).values
+    err = (pooled.double() - want).abs().max() / want.abs().max()
+    assert err < (5e-6 if x3 else 2e-3), err.item()
