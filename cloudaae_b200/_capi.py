@@ -65,8 +65,8 @@ _SIGNATURES = {
     "caae_bn_act_bwd_reduce": "iipipppppiifipp" "p",
     "caae_bn_act_bwd_apply": "iipippppppiifippi" "p",
     "caae_colsum": "iipip" "p",
-    "caae_fc_bn_fwd": "iipipppppppppipi" "p",
-    "caae_fc_bn_bwd": "iipipppppipipipp" "p",
+    "caae_fc_bn_fwd": "iipipppppppppipip" "p",
+    "caae_fc_bn_bwd": "iipipppppipipippp" "p",
     "caae_add3": "lpppp" "p",
     "caae_edge_fold_weights": "iippppi" "p",
     "caae_edge_unfold_wgrad": "iipip" "p",

@@ -34,7 +34,7 @@ fc_bn_fwd_kernel(int R, int C, const float* __restrict__ Y, int ld, const float*
                  const float* __restrict__ beta, float* __restrict__ ema_mean, float* __restrict__ ema_var,
                  const float* __restrict__ decay, float* __restrict__ scale, float* __restrict__ shift,
                  float* __restrict__ save_mean, float* __restrict__ save_invstd, int relu, float* __restrict__ out,
-                 int ldo) {
+                 int ldo, float* __restrict__ out_lo) {
   __shared__ double s_a[FC_LANES][33], s_b[FC_LANES][33];
   __shared__ float s_sc[32], s_sh[32];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -69,6 +69,7 @@ fc_bn_fwd_kernel(int R, int C, const float* __restrict__ Y, int ld, const float*
       float v = fmaf(Y[(size_t)r * ld + ch], sc, sh);
       if (relu) v = fmaxf(v, 0.f);
       out[(size_t)r * ldo + ch] = v;
+      if (out_lo != nullptr) out_lo[(size_t)r * ldo + ch] = v - tf32_rne(v);   // low part for the split-precision GEMM behind
     }
   }
 }
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(1024)
 fc_bn_bwd_kernel(int R, int C, const float* __restrict__ Y, int ld, const float* __restrict__ scale,
                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ gamma, int relu, const float* dOut, int lddo, float* dY, int lddy,
-                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dY_lo) {
   __shared__ double s_a[FC_LANES][33], s_b[FC_LANES][33];
   __shared__ float s_c0[32], s_c1[32];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -112,7 +113,9 @@ fc_bn_bwd_kernel(int R, int C, const float* __restrict__ Y, int ld, const float*
       const float y = Y[(size_t)r * ld + ch];
       const bool on = !relu || fmaf(y, sc, sh) > 0.f;
       const float dy = on ? dOut[(size_t)r * lddo + ch] : 0.f;
-      dY[(size_t)r * lddy + ch] = gis * (dy - mdy - (y - mu) * is * mdz);
+      const float d = gis * (dy - mdy - (y - mu) * is * mdz);
+      dY[(size_t)r * lddy + ch] = d;
+      if (dY_lo != nullptr) dY_lo[(size_t)r * lddy + ch] = d - tf32_rne(d);
     }
   }
 }
@@ -149,24 +152,25 @@ using namespace caae;
 
 extern "C" int caae_fc_bn_fwd(int R, int C, const float* Y, int ld, const float* gamma, const float* beta,
                               float* ema_mean, float* ema_var, const float* decay, float* scale, float* shift,
-                              float* save_mean, float* save_invstd, int relu, float* out, int ldo,
+                              float* save_mean, float* save_invstd, int relu, float* out, int ldo, float* out_lo,
                               caae_stream_t stream) {
   CAAE_RETURN_IF(R <= 0 || C <= 0 || ld < C || (out && ldo < C), CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!Y || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd, CAAE_E_NULLPTR);
   CAAE_RETURN_IF((ema_mean == nullptr) != (ema_var == nullptr), CAAE_E_NULLPTR);
   fc_bn_fwd_kernel<<<(C + 31) / 32, dim3(32, FC_LANES), 0, as_stream(stream)>>>(
-      R, C, Y, ld, gamma, beta, ema_mean, ema_var, decay, scale, shift, save_mean, save_invstd, relu, out, ldo);
+      R, C, Y, ld, gamma, beta, ema_mean, ema_var, decay, scale, shift, save_mean, save_invstd, relu, out, ldo, out_lo);
   return CAAE_LAUNCH_STATUS();
 }
 
 extern "C" int caae_fc_bn_bwd(int R, int C, const float* Y, int ld, const float* scale, const float* shift,
                               const float* mean, const float* invstd, const float* gamma, int relu, const float* dOut,
-                              int lddo, float* dY, int lddy, float* dgamma, float* dbeta, caae_stream_t stream) {
+                              int lddo, float* dY, int lddy, float* dgamma, float* dbeta, float* dY_lo,
+                              caae_stream_t stream) {
   CAAE_RETURN_IF(R <= 0 || C <= 0 || ld < C || lddo < C || lddy < C, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!Y || !scale || !shift || !mean || !invstd || !gamma || !dOut || !dY || !dgamma || !dbeta,
                  CAAE_E_NULLPTR);
   fc_bn_bwd_kernel<<<(C + 31) / 32, dim3(32, FC_LANES), 0, as_stream(stream)>>>(
-      R, C, Y, ld, scale, shift, mean, invstd, gamma, relu, dOut, lddo, dY, lddy, dgamma, dbeta);
+      R, C, Y, ld, scale, shift, mean, invstd, gamma, relu, dOut, lddo, dY, lddy, dgamma, dbeta, dY_lo);
   return CAAE_LAUNCH_STATUS();
 }
 

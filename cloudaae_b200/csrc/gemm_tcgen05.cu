@@ -972,7 +972,7 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
   }
   int splits = 1;
   const int tiles = tiles_m * tiles_n;
-  if (tiles < kNumSMs && num_kb >= 8 && !x3) {   // (the three passes of an x3 product share one accumulator: no split-K)
+  if (tiles < kNumSMs && num_kb >= 8) {   // (an x3 product runs its three passes over each split's own K range)
     splits = (2 * kNumSMs + tiles - 1) / tiles;
     // >= 16 K blocks per split when K is long: with 147 splits of 7 blocks the [64,256] EdgeConv weight gradient
     // spent its time in prologues and in 147-way contended reductions (57 us for 1 GFLOP)

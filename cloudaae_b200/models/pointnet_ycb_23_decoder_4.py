@@ -242,6 +242,16 @@ class _Engine:
         self.pool_parts = torch.empty(4 * batch * 1024, dtype=torch.float32, device=self.dev)   # pooled-epilogue scratch
         self.d_emb_br = _take(3 * B, 1024).view(3, B, 1024)
         self._heads_pending = False
+        # FC stack on the tensor cores (split-precision product): low parts of the weights (one pass over the FC range
+        # of the flat parameter buffer per forward), of the activations (written by the BN kernels) and of the gradients
+        fc_scopes = [s for br in self.branches for s in br]
+        self.fc_tc = self.x3 and os.environ.get("CLOUDAAE_FC_TC", "1") != "0" and B >= 64
+        self.fc_lo_start = min(variables.index[f"{s}/weights"][0] for s in fc_scopes)
+        self.flat_lo = torch.empty_like(variables.flat) if self.fc_tc else None
+        self.emb_lo = torch.empty(B, 1024, **f32)
+        self.fc_a_lo = {s: torch.empty_like(t) for s, t in self.fc_a.items()}
+        self.fc_d_lo = {s: torch.empty_like(t) for s, t in self.fc_d.items()}
+        self.d_out_lo = [torch.empty(B, self.scopes[br[-1]][1], **f32) for br in self.branches]
 
     # -- helpers
     def _st(self):
@@ -264,26 +274,45 @@ class _Engine:
     def _on(self, s):
         return torch.cuda.stream(s) if s is not None else contextlib.nullcontext()
 
-    def _fc_fwd(self, scope, x, training, decay):
+    def _w_lo(self, scope):
+        o, shape = self.v.index[f"{scope}/weights"]
+        return self.flat_lo[o:o + shape[0] * shape[1]].view(shape)
+
+    def _fc_gemm(self, ta, tb, M, N, K, A, A_lo, lda, Bm, B_lo, ldb, C, ldc, bias=None, acc=0):
+        """A contraction of the FC stack (M or K = batch).  Tensor cores with the split-precision product when the
+        output is at least a tile wide — fp32-grade, so the batch norm over `batch` rows behind it sees the same
+        values as the FFMA path; the 3-wide pose outputs and tiny batches stay on the FFMA kernel."""
+        if (self.fc_tc and A_lo is not None and B_lo is not None and N >= 128 and M >= 64 and K >= 64 and
+                self.lib.caae_gemm_tf32_supported(ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb)):
+            self._c("caae_gemm_tf32x3", ta, tb, M, N, K, self._p(A), self._p(A_lo), lda, self._p(Bm), self._p(B_lo), ldb,
+                    self._p(C), ldc, self._p(bias), acc, None)
+        else:
+            self._gemm(ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc, bias, acc)
+
+    def _fc_fwd(self, scope, x, x_lo, training, decay):
         """One fully connected layer on [B, fin]: y = x W + b, then training-mode BN + ReLU in one launch
-        (tf_util.fully_connected, :321-365)."""
+        (tf_util.fully_connected, :321-365).  Returns (activation, its low part)."""
         fin, fout, has_bn = self.scopes[scope]
         B, v = self.B, self.v
         y = self.fc_y[scope]
-        self._gemm(0, 0, B, fout, fin, x, fin, v[f"{scope}/weights"], fout, y, fout, v[f"{scope}/biases"], 1)
+        self._fc_gemm(0, 0, B, fout, fin, x, x_lo, fin, v[f"{scope}/weights"], self._w_lo(scope) if self.fc_tc else None, fout,
+                      y, fout, v[f"{scope}/biases"], 1)
         if not has_bn:
-            return None
+            return None, None
         bn, a = self.bn[scope], self.fc_a[scope]
+        a_lo = self.fc_a_lo[scope] if self.fc_tc else None
         if training:
             self._c("caae_fc_bn_fwd", B, fout, self._p(y), fout, self._p(v[f"{scope}/bn/gamma"]),
                     self._p(v[f"{scope}/bn/beta"]), self._p(v[f"{scope}/bn/ema_mean"]), self._p(v[f"{scope}/bn/ema_var"]),
                     self._p(decay), self._p(bn["scale"]), self._p(bn["shift"]), self._p(bn["mean"]),
-                    self._p(bn["invstd"]), 1, self._p(a), fout)
+                    self._p(bn["invstd"]), 1, self._p(a), fout, self._p(a_lo))
         else:
             self._bn_coeffs(scope, False, 1, B, decay)
             self._c("caae_bn_act", B, fout, self._p(y), fout, self._p(bn["scale"]), self._p(bn["shift"]), 1,
                     self._p(a), fout)
-        return a
+            if a_lo is not None:
+                self._split(a, fout, B, fout, a_lo, fout)
+        return a, a_lo
 
     def _fc_bn_bwd(self, scope, d):
         """BN + ReLU backward of an FC layer, in place over d [B, fout]; bn/gamma, bn/beta gradients."""
@@ -291,7 +320,8 @@ class _Engine:
         bn, v = self.bn[scope], self.v
         self._c("caae_fc_bn_bwd", self.B, C, self._p(self.fc_y[scope]), C, self._p(bn["scale"]), self._p(bn["shift"]),
                 self._p(bn["mean"]), self._p(bn["invstd"]), self._p(v[f"{scope}/bn/gamma"]), 1, self._p(d), C,
-                self._p(d), C, self._p(v.grad_of(f"{scope}/bn/gamma")), self._p(v.grad_of(f"{scope}/bn/beta")))
+                self._p(d), C, self._p(v.grad_of(f"{scope}/bn/gamma")), self._p(v.grad_of(f"{scope}/bn/beta")),
+                self._p(self.fc_d_lo[scope] if self.fc_tc else None))
 
     def _branch_backward(self, bi, d_out):
         """Backward of FC branch `bi` on the current stream; its weight gradients on their own stream.
@@ -302,23 +332,31 @@ class _Engine:
         w = self.s_wgrad[bi] if self.concurrent else None
         d_out = d_out.contiguous()
         d2, d1 = self.fc_d[s2], self.fc_d[s1]
+        tc = self.fc_tc
+        lo = lambda t: t if tc else None  # noqa: E731
+        d_out_lo = None
+        if tc and f3[1] >= 128:           # the decoder's 3072-wide output gradient (the pose heads' are 3 wide: FFMA)
+            d_out_lo = self.d_out_lo[bi]
+            self._split(d_out, f3[1], B, f3[1], d_out_lo, f3[1])
+        W3, W2, W1 = (self.v[f"{s_}/weights"] for s_ in (s3, s2, s1))
+        W3l, W2l, W1l = ((self._w_lo(s_) if tc else None) for s_ in (s3, s2, s1))
         # linear output layer
         if w is not None: self._fork(w)
         with self._on(w):
-            self._dense_wgrad(s3, self.fc_a[s2], f3[0], B, d_out, True)
-        self._gemm(0, 1, B, f3[0], f3[1], d_out, f3[1], self.v[f"{s3}/weights"], f3[1], d2, f3[0], None, 1)
+            self._fc_wgrad(s3, self.fc_a[s2], lo(self.fc_a_lo[s2]), f3[0], B, d_out, d_out_lo, True)
+        self._fc_gemm(0, 1, B, f3[0], f3[1], d_out, d_out_lo, f3[1], W3, W3l, f3[1], d2, f3[0], None, 1)
         # fc2: BN+ReLU backward, wgrad, dgrad
         self._fc_bn_bwd(s2, d2)
         if w is not None: self._fork(w)
         with self._on(w):
-            self._dense_wgrad(s2, self.fc_a[s1], f2[0], B, d2, False)
-        self._gemm(0, 1, B, f2[0], f2[1], d2, f2[1], self.v[f"{s2}/weights"], f2[1], d1, f2[0], None, 1)
+            self._fc_wgrad(s2, self.fc_a[s1], lo(self.fc_a_lo[s1]), f2[0], B, d2, lo(self.fc_d_lo[s2]), False)
+        self._fc_gemm(0, 1, B, f2[0], f2[1], d2, lo(self.fc_d_lo[s2]), f2[1], W2, W2l, f2[1], d1, f2[0], None, 1)
         # fc1
         self._fc_bn_bwd(s1, d1)
         if w is not None: self._fork(w)
         with self._on(w):
-            self._dense_wgrad(s1, self.emb, f1[0], B, d1, False)
-        self._gemm(0, 1, B, f1[0], f1[1], d1, f1[1], self.v[f"{s1}/weights"], f1[1], self.d_emb_br[bi], f1[0], None, 1)
+            self._fc_wgrad(s1, self.emb, lo(self.emb_lo), f1[0], B, d1, lo(self.fc_d_lo[s1]), False)
+        self._fc_gemm(0, 1, B, f1[0], f1[1], d1, lo(self.fc_d_lo[s1]), f1[1], W1, W1l, f1[1], self.d_emb_br[bi], f1[0], None, 1)
         if w is not None: self._join(w)
 
     def backward_heads_async(self, d_rot, d_trans):
@@ -448,6 +486,12 @@ class _Engine:
                 self._p(bn["mean"]), self._p(bn["invstd"]), self._p(bn["coef"]), self._p(d_out), ldo, group,
                 float(gscale), 1, self._p(argmax), self._p(d_y), C)
 
+    def _fc_wgrad(self, scope, x, x_lo, ldx, R, d_y, d_y_lo, bias_grad):
+        fin, fout, _ = self.scopes[scope]
+        self._fc_gemm(1, 0, fin, fout, R, x, x_lo, ldx, d_y, d_y_lo, fout, self.v.grad_of(f"{scope}/weights"), fout)
+        if bias_grad:
+            self._c("caae_colsum", R, fout, self._p(d_y), fout, self._p(self.v.grad_of(f"{scope}/biases")))
+
     def _dense_wgrad(self, scope, x, ldx, R, d_y, bias_grad):
         fin, fout, _ = self.scopes[scope]
         self._gemm(1, 0, fin, fout, R, x, ldx, d_y, fout, self.v.grad_of(f"{scope}/weights"), fout)
@@ -467,6 +511,9 @@ class _Engine:
         if se is not None: self._fork(se)
         with self._on(se):   # accumulation targets of the FC stack's split-K GEMMs (forward and backward)
             self._c("caae_fill_f32", self.fc_acc_flat.numel(), self._p(self.fc_acc_flat), 0.0)
+            if self.fc_tc:       # low parts of every FC weight: one pass over the FC range of the flat parameter buffer
+                n_fc = self.v.flat.numel() - self.fc_lo_start
+                self._split(self.v.flat[self.fc_lo_start:], n_fc, 1, n_fc, self.flat_lo[self.fc_lo_start:], n_fc)
             if self.x3:          # low parts of the conv weights that take the split-precision tensor-core product
                 for s_, lo in self.w_lo.items():
                     fin_, fout_, _ = self.scopes[s_]
@@ -546,13 +593,15 @@ class _Engine:
 
     def forward_fc(self, train_fc: bool, decay):
         """embedding -> the three FC branches (decoder, rotation head, translation head)."""
+        if self.fc_tc:
+            self._split(self.emb, 1024, self.B, 1024, self.emb_lo, 1024)
         for bi in (1, 2, 0):   # heads on side streams, the decoder on the caller's
             st = self.s_branch[bi - 1] if (self.concurrent and bi > 0) else None
             if st is not None: self._fork(st)
             with self._on(st):
-                inp = self.emb
+                inp, inp_lo = self.emb, (self.emb_lo if self.fc_tc else None)
                 for s in self.branches[bi]:
-                    inp = self._fc_fwd(s, inp, train_fc, decay)
+                    inp, inp_lo = self._fc_fwd(s, inp, inp_lo, train_fc, decay)
         for st in self.s_branch:
             self._join(st)
 

@@ -194,10 +194,12 @@ int caae_colsum(int R, int C, const float* X, int ld, float* out, caae_stream_t 
  * NULL).  bwd: dY = BN/ReLU backward of dOut (dY may alias dOut), dgamma, dbeta. */
 int caae_fc_bn_fwd(int R, int C, const float* Y, int ld, const float* gamma, const float* beta, float* ema_mean,
                    float* ema_var, const float* decay, float* scale, float* shift, float* save_mean,
-                   float* save_invstd, int relu, float* out, int ldo, caae_stream_t stream);
+                   float* save_invstd, int relu, float* out, int ldo, float* out_lo /* out - tf32(out), may be NULL */,
+                   caae_stream_t stream);
 int caae_fc_bn_bwd(int R, int C, const float* Y, int ld, const float* scale, const float* shift, const float* mean,
                    const float* invstd, const float* gamma, int relu, const float* dOut, int lddo, float* dY,
-                   int lddy, float* dgamma, float* dbeta, caae_stream_t stream);
+                   int lddy, float* dgamma, float* dbeta, float* dY_lo /* dY - tf32(dY), may be NULL */,
+                   caae_stream_t stream);
 /* out = a + b + c, n elements (sum of the three branches' gradients w.r.t. the embedding) */
 int caae_add3(long n, const float* a, const float* b, const float* c, float* out, caae_stream_t stream);
 
