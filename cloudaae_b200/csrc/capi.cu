@@ -42,3 +42,11 @@ extern "C" unsigned int caae_crc32c(unsigned int crc, const void* data, unsigned
   while (n--) c = tbl[0][(c ^ *p++) & 0xFFu] ^ (c >> 8);
   return ~c;
 }
+
+#include <stdlib.h>
+namespace caae {
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CAAE_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+}  // namespace caae

@@ -35,4 +35,30 @@ __device__ __forceinline__ float tf32_rne(float x) {
 
 inline cudaStream_t as_stream(caae_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// A train step is ~125 short kernels, ~70 of them on one dependent chain: what separates them is launch latency, not
+// work.  Every kernel starts with pdl_wait() (griddepcontrol.wait: block until the preceding kernel of the stream has
+// completed and flushed — a no-op for a normal launch) and is launched with the programmatic-stream-serialization
+// attribute, so its CTAs are scheduled and run their prologue while the predecessor drains.  Because the wait is the
+// FIRST statement, ordering semantics are exactly those of a normal launch.  CAAE_PDL=0 launches normally.
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+bool pdl_enabled();   // capi.cu
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // (a launch error is picked up by CAAE_LAUNCH_STATUS)
+}
+
 }  // namespace caae

@@ -35,6 +35,7 @@ fc_bn_fwd_kernel(int R, int C, const float* __restrict__ Y, int ld, const float*
                  const float* __restrict__ decay, float* __restrict__ scale, float* __restrict__ shift,
                  float* __restrict__ save_mean, float* __restrict__ save_invstd, int relu, float* __restrict__ out,
                  int ldo, float* __restrict__ out_lo) {
+  pdl_wait();
   __shared__ double s_a[FC_LANES][33], s_b[FC_LANES][33];
   __shared__ float s_sc[32], s_sh[32];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -81,6 +82,7 @@ fc_bn_bwd_kernel(int R, int C, const float* __restrict__ Y, int ld, const float*
                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ gamma, int relu, const float* dOut, int lddo, float* dY, int lddy,
                  float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dY_lo) {
+  pdl_wait();
   __shared__ double s_a[FC_LANES][33], s_b[FC_LANES][33];
   __shared__ float s_c0[32], s_c1[32];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -123,6 +125,7 @@ fc_bn_bwd_kernel(int R, int C, const float* __restrict__ Y, int ld, const float*
 // out[c] = sum_r X[r][c] in a fixed order (bias gradients of the linear output layers)
 __global__ void __launch_bounds__(1024)
 fc_colsum_kernel(int R, int C, const float* __restrict__ X, int ld, float* __restrict__ out) {
+  pdl_wait();
   __shared__ float s_v[FC_LANES][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * 32 + tx;
@@ -142,6 +145,7 @@ fc_colsum_kernel(int R, int C, const float* __restrict__ X, int ld, float* __res
 // out = a + b + c (the three branches' gradients w.r.t. the embedding)
 __global__ void add3_kernel(long n, const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                             float* __restrict__ out) {
+  pdl_wait();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x)
     out[e] = (a[e] + b[e]) + c[e];
 }
@@ -157,7 +161,7 @@ extern "C" int caae_fc_bn_fwd(int R, int C, const float* Y, int ld, const float*
   CAAE_RETURN_IF(R <= 0 || C <= 0 || ld < C || (out && ldo < C), CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!Y || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd, CAAE_E_NULLPTR);
   CAAE_RETURN_IF((ema_mean == nullptr) != (ema_var == nullptr), CAAE_E_NULLPTR);
-  fc_bn_fwd_kernel<<<(C + 31) / 32, dim3(32, FC_LANES), 0, as_stream(stream)>>>(
+  caae::launch(fc_bn_fwd_kernel, (C + 31) / 32, dim3(32, FC_LANES), 0, as_stream(stream), 
       R, C, Y, ld, gamma, beta, ema_mean, ema_var, decay, scale, shift, save_mean, save_invstd, relu, out, ldo, out_lo);
   return CAAE_LAUNCH_STATUS();
 }
@@ -169,7 +173,7 @@ extern "C" int caae_fc_bn_bwd(int R, int C, const float* Y, int ld, const float*
   CAAE_RETURN_IF(R <= 0 || C <= 0 || ld < C || lddo < C || lddy < C, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!Y || !scale || !shift || !mean || !invstd || !gamma || !dOut || !dY || !dgamma || !dbeta,
                  CAAE_E_NULLPTR);
-  fc_bn_bwd_kernel<<<(C + 31) / 32, dim3(32, FC_LANES), 0, as_stream(stream)>>>(
+  caae::launch(fc_bn_bwd_kernel, (C + 31) / 32, dim3(32, FC_LANES), 0, as_stream(stream), 
       R, C, Y, ld, scale, shift, mean, invstd, gamma, relu, dOut, lddo, dY, lddy, dgamma, dbeta, dY_lo);
   return CAAE_LAUNCH_STATUS();
 }
@@ -177,7 +181,7 @@ extern "C" int caae_fc_bn_bwd(int R, int C, const float* Y, int ld, const float*
 extern "C" int caae_colsum(int R, int C, const float* X, int ld, float* out, caae_stream_t stream) {
   CAAE_RETURN_IF(R < 0 || C <= 0 || ld < C, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!X || !out, CAAE_E_NULLPTR);
-  fc_colsum_kernel<<<(C + 31) / 32, dim3(32, FC_LANES), 0, as_stream(stream)>>>(R, C, X, ld, out);
+  caae::launch(fc_colsum_kernel, (C + 31) / 32, dim3(32, FC_LANES), 0, as_stream(stream), R, C, X, ld, out);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -187,6 +191,6 @@ extern "C" int caae_add3(long n, const float* a, const float* b, const float* c,
   CAAE_RETURN_IF(!a || !b || !c || !out, CAAE_E_NULLPTR);
   long blocks = (n + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  add3_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(n, a, b, c, out);
+  caae::launch(add3_kernel, (int)blocks, 256, 0, as_stream(stream), n, a, b, c, out);
   return CAAE_LAUNCH_STATUS();
 }

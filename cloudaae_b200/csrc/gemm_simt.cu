@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(GTHREADS)
 gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                  float* __restrict__ C, int ldc, const float* __restrict__ bias, int accumulate, int k_per_split,
                  int use_atomics) {
+  pdl_wait();
   __shared__ __align__(16) float As[GBK][GBM + 4];
   __shared__ __align__(16) float Bs[GBK][GBN + 4];
 
@@ -127,6 +128,7 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
 }
 
 __global__ void zero_matrix_kernel(int M, int N, float* __restrict__ C, int ldc) {
+  pdl_wait();
   const long total = (long)M * N;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
     C[(e / N) * ldc + (e % N)] = 0.f;
@@ -159,11 +161,11 @@ extern "C" int caae_gemm_f32(int transa, int transb, int M, int N, int K, const 
   if (use_atomics && !accumulate) {
     long total = (long)M * N;
     int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    zero_matrix_kernel<<<blocks, 256, 0, s>>>(M, N, C, ldc);
+    caae::launch(zero_matrix_kernel, blocks, 256, 0, s, M, N, C, ldc);
   }
   dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, splits);
   CAAE_RETURN_IF(grid.y > 65535 || grid.z > 65535, CAAE_E_BADSHAPE);
-#define LAUNCH(TA, TB) gemm_simt_kernel<TA, TB><<<grid, GTHREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, k_per_split, use_atomics)
+#define LAUNCH(TA, TB) caae::launch(gemm_simt_kernel<TA, TB>, grid, GTHREADS, 0, s, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, k_per_split, use_atomics)
   if (transa) { if (transb) LAUNCH(true, true); else LAUNCH(true, false); }
   else        { if (transb) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(TTHREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
+  pdl_wait();
   __shared__ __align__(16) float s_bias[TBN];
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-byte alignment
@@ -277,6 +278,7 @@ template <int BN, int MH_, bool A_MN>
 __global__ void __launch_bounds__(BIG_THREADS)
 gemm_tf32_big_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+  pdl_wait();
   using Cfg = BigCfg<BN, MH_>;
   constexpr int ST = Cfg::STAGES, MH = Cfg::MH;
   __shared__ __align__(16) float s_bias[BN];
@@ -496,6 +498,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                          const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p, const int tiles_m,
                          const int tiles_n) {
+  pdl_wait();
   using Cfg = PsCfg<X3>;
   constexpr int ST = Cfg::STAGES;
   __shared__ __align__(16) float s_bias[Cfg::BIAS_SMEM];
@@ -748,6 +751,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 
 // lo = x - tf32_rne(x): the low part of a split-precision operand (exact in fp32).  [rows, cols] with row pitches.
 __global__ void split_tf32_kernel(long rows, int cols, const float* __restrict__ x, int ldx, float* __restrict__ lo, int ldlo) {
+  pdl_wait();
   const long total = rows * cols;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const long r = e / cols;
@@ -758,6 +762,7 @@ __global__ void split_tf32_kernel(long rows, int cols, const float* __restrict__
 }
 
 __global__ void zero_matrix2_kernel(int M, int N, float* __restrict__ C, int ldc) {
+  pdl_wait();
   const long total = (long)M * N;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
     C[(e / N) * ldc + (e % N)] = 0.f;
@@ -910,9 +915,9 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
     p.kb_per_split = num_kb; p.atomic = 0; p.accumulate = accumulate;
     const int ctas = tm * tn < kNumSMs ? tm * tn : kNumSMs;
     if (x3)   // (the *_lo maps built above have the same boxes as map_a2 / map_b2: K-major A, either-major B)
-      gemm_tf32_persist_kernel<true><<<ctas, BIG_THREADS, PsCfg<true>::SMEM, s>>>(map_a2, map_b2, map_c2, map_a_lo, map_b_lo, p, tm, tn);
+      caae::launch(gemm_tf32_persist_kernel<true>, ctas, BIG_THREADS, PsCfg<true>::SMEM, s, map_a2, map_b2, map_c2, map_a_lo, map_b_lo, p, tm, tn);
     else
-      gemm_tf32_persist_kernel<false><<<ctas, BIG_THREADS, PsCfg<false>::SMEM, s>>>(map_a2, map_b2, map_c2, map_a2, map_b2, p, tm, tn);
+      caae::launch(gemm_tf32_persist_kernel<false>, ctas, BIG_THREADS, PsCfg<false>::SMEM, s, map_a2, map_b2, map_c2, map_a2, map_b2, p, tm, tn);
     return CAAE_LAUNCH_STATUS();
   }
   // the three big dgcnn_agg-shaped contractions: large tiles, one CTA per SM (see gemm_tf32_big_kernel)
@@ -947,7 +952,7 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
     if (p.atomic && !accumulate) {
       const long total = (long)M * N;
       const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-      zero_matrix2_kernel<<<blocks, 256, 0, s>>>(M, N, C, ldc);
+      caae::launch(zero_matrix2_kernel, blocks, 256, 0, s, M, N, C, ldc);
     }
     dim3 grid(N / bn, (M + mh * TBM - 1) / (mh * TBM), sp);
     CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
@@ -963,7 +968,7 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
       cudaError_t e_ = cudaFuncSetAttribute(gemm_tf32_big_kernel<BN_, MH_, AMN_>,                                    \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BigCfg<BN_, MH_>::SMEM); \
       if (e_ != cudaSuccess) return (int)e_;                                                                         \
-      gemm_tf32_big_kernel<BN_, MH_, AMN_><<<grid, BIG_THREADS, BigCfg<BN_, MH_>::SMEM, s>>>(map_a2, map_b2, map_c2, p);        \
+      caae::launch(gemm_tf32_big_kernel<BN_, MH_, AMN_>, grid, BIG_THREADS, BigCfg<BN_, MH_>::SMEM, s, map_a2, map_b2, map_c2, p);        \
     } while (0)
     if (big_wgrad) CAAE_LAUNCH_BIG(128, 3, true);
     else CAAE_LAUNCH_BIG(160, 2, false);
@@ -987,7 +992,7 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
   if (p.atomic && !accumulate) {
     const long total = (long)M * N;
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    zero_matrix2_kernel<<<blocks, 256, 0, s>>>(M, N, C, ldc);
+    caae::launch(zero_matrix2_kernel, blocks, 256, 0, s, M, N, C, ldc);
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -1006,7 +1011,7 @@ static int gemm_tf32_impl(int transa, int transb, int M, int N, int K, const flo
     if (rc) return rc;
     p.tma_store = p.accumulate ? 2 : 1;
   }
-  gemm_tf32_kernel<<<grid, TTHREADS, TSMEM_BYTES, s>>>(map_a, map_b, map_c, map_a_lo, map_b_lo, p);
+  caae::launch(gemm_tf32_kernel, grid, TTHREADS, TSMEM_BYTES, s, map_a, map_b, map_c, map_a_lo, map_b_lo, p);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -1031,7 +1036,7 @@ extern "C" int caae_split_tf32(long rows, int cols, const float* x, int ldx, flo
   const long total = rows * cols;
   long blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  split_tf32_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(rows, cols, x, ldx, lo, ldlo);
+  caae::launch(split_tf32_kernel, (int)blocks, 256, 0, as_stream(stream), rows, cols, x, ldx, lo, ldlo);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -1042,6 +1047,7 @@ extern "C" int caae_split_tf32(long rows, int cols, const float* x, int ldx, flo
 // 2 = max.  parts f32[ceil(M / 256) * 4][N] is scratch.  Split-precision product when A_lo / B_lo are given.
 __global__ void pool_finalize_kernel(int groups, int N, const float* __restrict__ parts, int mode, float inv_group,
                                      float* __restrict__ pooled) {
+  pdl_wait();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)groups * N; e += (long)gridDim.x * blockDim.x) {
     const long g = e / N;
     const int c = (int)(e - g * N);
@@ -1064,7 +1070,7 @@ extern "C" int caae_gemm_tf32_pool(int M, int N, int K, const float* A, const fl
   const int rc = gemm_tf32_impl(0, 0, M, N, K, A, lda, B, ldb, parts, N, bias, 0, nullptr, stream, A_lo, B_lo, &pe);
   if (rc) return rc;
   const long total = (long)(M / group) * N;
-  pool_finalize_kernel<<<(int)((total + 255) / 256), 256, 0, as_stream(stream)>>>(M / group, N, parts, mode, 1.f / (float)group, pooled);
+  caae::launch(pool_finalize_kernel, (int)((total + 255) / 256), 256, 0, as_stream(stream), M / group, N, parts, mode, 1.f / (float)group, pooled);
   return CAAE_LAUNCH_STATUS();
 }
 

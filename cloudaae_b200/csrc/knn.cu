@@ -39,6 +39,7 @@ __device__ __forceinline__ uint32_t sortable(float f) {
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __restrict__ idx_out,
            const int* __restrict__ only) {
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   float* XT = smem;                               // [c][KNN_XT_LD]
   float* QT = XT + (size_t)c * KNN_XT_LD;         // [c][KNN_QT_LD]
@@ -273,7 +274,7 @@ static int knn_impl(int b, int n, int c, int k, const float* x, int ldx, int* id
   else if (part == 2 && !tc) return CAAE_OK;             // ... and part 2 has nothing left to do
   if (tc && part != 2)
     return knn_tc_launch(b, n, c, k, x, ldx, idx, part == 1 ? flags : nullptr, as_stream(stream));
-  knn_kernel<<<grid, KNN_THREADS, smem, as_stream(stream)>>>(n, c, k, x, ldx, idx, part == 2 ? flags : nullptr);
+  caae::launch(knn_kernel, grid, KNN_THREADS, smem, as_stream(stream), n, c, k, x, ldx, idx, part == 2 ? flags : nullptr);
   return CAAE_LAUNCH_STATUS();
 }
 

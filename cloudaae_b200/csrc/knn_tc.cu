@@ -40,6 +40,7 @@ template <int CPAD>   // channels padded to 32 or 64 (zero columns change neithe
 __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tc_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __restrict__ idx_out,
               const int* __restrict__ skip, int* __restrict__ dbg_cnt) {
+  pdl_wait();
   constexpr int NS = CPAD / 32;                       // slabs
   constexpr uint32_t OPER = NS * KT_SLAB;             // bytes of one operand half (H or L)
   extern __shared__ uint8_t kt_smem_raw[];
@@ -376,7 +377,7 @@ static int launch_knn_tc(int b, int n, int c, int k, const float* x, int ldx, in
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  knn_tc_kernel<CPAD><<<b, KT_THREADS, smem, s>>>(n, c, k, x, ldx, idx, skip, dbg_cnt);
+  caae::launch(knn_tc_kernel<CPAD>, b, KT_THREADS, smem, s, n, c, k, x, ldx, idx, skip, dbg_cnt);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -395,6 +396,7 @@ int knn_tc_launch(int b, int n, int c, int k, const float* x, int ldx, int* idx,
 constexpr int KC_SLOTS = 1024;
 __global__ void __launch_bounds__(256)
 knn_classify_kernel(int n, int c, const float* __restrict__ x, int ldx, int* __restrict__ flags) {
+  pdl_wait();
   __shared__ int table[KC_SLOTS];
   __shared__ int dups;
   const int cloud = blockIdx.x, tid = threadIdx.x;
@@ -426,7 +428,7 @@ int knn_tc_debug_counts(int b, int n, int c, int k, const float* x, int ldx, int
 }
 
 int knn_classify_launch(int b, int n, int c, const float* x, int ldx, int* flags, cudaStream_t s) {
-  knn_classify_kernel<<<b, 256, 0, s>>>(n, c, x, ldx, flags);
+  caae::launch(knn_classify_kernel, b, 256, 0, s, n, c, x, ldx, flags);
   return CAAE_LAUNCH_STATUS();
 }
 

@@ -34,6 +34,7 @@ edge_reduce_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldp
                    const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ mean, const float* __restrict__ invstd,
                    const float* __restrict__ dOut, int lddo, double* __restrict__ parts) {
+  pdl_wait();
   __shared__ int s_idx[EDGE_PTS * 32];
   __shared__ double s_a[8][32], s_b[8][32];
   const int cloud = blockIdx.y, p0 = blockIdx.x * EDGE_PTS;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256)
 edge_apply_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq, const int* __restrict__ idx,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ldo,
                   float* __restrict__ out_lo) {
+  pdl_wait();
   __shared__ int s_idx[EDGE_PTS * 32];
   const int cloud = blockIdx.y, p0 = blockIdx.x * EDGE_PTS;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
@@ -115,6 +117,7 @@ edge_bwd_apply_kernel(int n, int k, int cout, const float* __restrict__ PQ, int 
                       const float* __restrict__ mean, const float* __restrict__ invstd,
                       const float* __restrict__ coef, const float* __restrict__ dOut, int lddo,
                       float* __restrict__ dPQ, int lddpq) {
+  pdl_wait();
   __shared__ int s_idx[EDGE_PTS * 32];
   const int cloud = blockIdx.y, p0 = blockIdx.x * EDGE_PTS;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
@@ -155,6 +158,7 @@ col_reduce_kernel(int R, int C, const float* __restrict__ Y, int ld, const float
                   const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                   const float* __restrict__ dOut, int lddo, int group, float gscale, int relu,
                   const int* __restrict__ argmax, double* __restrict__ parts) {
+  pdl_wait();
   __shared__ double s_a[8][32], s_b[8][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * 32 + tx;
@@ -227,6 +231,7 @@ bn_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double c
                    const float* __restrict__ decay, float* __restrict__ scale,
                    float* __restrict__ shift, float* __restrict__ save_mean,
                    float* __restrict__ save_invstd) {
+  pdl_wait();
   const int ch = blockIdx.x * 32 + threadIdx.x;
   double s, ss;
   reduce_parts(C, parts, nparts, ch, s, ss);
@@ -252,6 +257,7 @@ bn_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double c
 __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ ema_mean, const float* __restrict__ ema_var,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= C) return;
   const float sc = gamma[ch] * rsqrtf(ema_var[ch] + kBnEps);
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(int C, const double* __restrict__ parts, int nparts, double count,
                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                        float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_wait();
   const int ch = blockIdx.x * 32 + threadIdx.x;
   double s, ss;
   reduce_parts(C, parts, nparts, ch, s, ss);
@@ -279,6 +286,7 @@ bn_bwd_finalize_kernel(int C, const double* __restrict__ parts, int nparts, doub
 __global__ void __launch_bounds__(256)
 bn_act_kernel(long total, int C, const float* __restrict__ Y, int ld, const float* __restrict__ scale,
               const float* __restrict__ shift, int relu, float* __restrict__ out, int ldo) {
+  pdl_wait();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const long r = e / C;
     const int ch = (int)(e - r * C);
@@ -293,6 +301,7 @@ template <bool MAXPOOL>
 __global__ void __launch_bounds__(256)
 bn_act_pool_kernel(int group, int C, const float* __restrict__ Y, int ld, const float* __restrict__ scale,
                    const float* __restrict__ shift, float* __restrict__ emb, int* __restrict__ argmax) {
+  pdl_wait();
   __shared__ float s_v[8][32];
   __shared__ int s_i[8][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -327,6 +336,7 @@ bn_act_pool_kernel(int group, int C, const float* __restrict__ Y, int ld, const 
 __global__ void __launch_bounds__(256)
 bn_act_meanpool_vec4_kernel(int group, int C, const float* __restrict__ Y, int ld, const float* __restrict__ scale,
                             const float* __restrict__ shift, float* __restrict__ emb) {
+  pdl_wait();
   __shared__ float4 s_v[8][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * 128 + tx * 4, g = blockIdx.y;
@@ -361,6 +371,7 @@ bn_act_bwd_kernel(long total, int C, const float* Y, int ld, const float* __rest
                   const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                   const float* __restrict__ coef, const float* __restrict__ dOut, int lddo, int group, float gscale,
                   int relu, const int* __restrict__ argmax, float* dY, int lddy) {
+  pdl_wait();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const long r = e / C;
     const int ch = (int)(e - r * C);
@@ -377,6 +388,7 @@ bn_act_bwd_kernel(long total, int C, const float* Y, int ld, const float* __rest
 __global__ void edge_fold_weights_kernel(int c, int cout, const float* __restrict__ w, int ldw,
                                          const float* __restrict__ bias, float* __restrict__ wf,
                                          float* __restrict__ bias_f) {
+  pdl_wait();
   const int total = c * cout;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int r = e / cout, o = e - r * cout;
@@ -390,6 +402,7 @@ __global__ void edge_fold_weights_kernel(int c, int cout, const float* __restric
 // gradient of the factorisation: dW_top = dWf_P, dW_bot = dWf_Q - dWf_P
 __global__ void edge_unfold_wgrad_kernel(int c, int cout, const float* __restrict__ dwf, int lddwf,
                                          float* __restrict__ dw) {
+  pdl_wait();
   const int total = c * cout;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int r = e / cout, o = e - r * cout;
@@ -409,6 +422,7 @@ col_reduce_vec4_kernel(int R, int C, const float* __restrict__ Y, int ld, const 
                        const float* __restrict__ shift, const float* __restrict__ mean,
                        const float* __restrict__ invstd, const float* __restrict__ dOut, int lddo, int group,
                        float gscale, int relu, const int* __restrict__ argmax, double* __restrict__ parts) {
+  pdl_wait();
   __shared__ double s_a[8][128], s_b[8][128];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * 128 + tx * 4;
@@ -474,6 +488,7 @@ bn_act_bwd_vec4_kernel(int R, int C, const float* Y, int ld, const float* __rest
                        const float* __restrict__ invstd, const float* __restrict__ coef,
                        const float* __restrict__ dOut, int lddo, int group, float gscale, int relu,
                        const int* __restrict__ argmax, float* dY, int lddy) {
+  pdl_wait();
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * 128 + tx * 4;
   const int r0 = blockIdx.y * COL_ROWS, r1 = min(R, r0 + COL_ROWS);
@@ -531,6 +546,7 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef, const float* __restrict__ dOut,
                   int lddo, float* __restrict__ out, int ldo, double* __restrict__ parts, float* __restrict__ out_lo) {
+  pdl_wait();
   extern __shared__ __align__(16) float es_smem[];
   float* Qs = es_smem;                                   // [n][ES_CH]
   float* dQs = Qs + (size_t)n * ES_CH;                   // [n][ES_CH] (MODE 3 only)
@@ -661,7 +677,7 @@ static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int
     if (e != cudaSuccess) return (int)e;
     smem_set = smem;
   }
-  edge_cloud_kernel<MODE><<<dim3(cout / ES_CH, b), dim3(32, 32), smem, s>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean,
+  caae::launch(edge_cloud_kernel<MODE>, dim3(cout / ES_CH, b), dim3(32, 32), smem, s, n, k, cout, PQ, ldpq, idx, scale, shift, mean,
                                                                           invstd, coef, dOut, lddo, out, ldo, parts, out_lo);
   return CAAE_LAUNCH_STATUS();
 }
@@ -698,7 +714,7 @@ extern "C" int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, i
                                 nullptr, 0, parts, as_stream(stream));
   }
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
-  edge_reduce_kernel<0><<<grid, block, 0, as_stream(stream)>>>(n, k, cout, PQ, ldpq, idx, nullptr, nullptr, nullptr,
+  caae::launch(edge_reduce_kernel<0>, grid, block, 0, as_stream(stream), n, k, cout, PQ, ldpq, idx, nullptr, nullptr, nullptr,
                                                                 nullptr, nullptr, 0, parts);
   return CAAE_LAUNCH_STATUS();
 }
@@ -715,7 +731,7 @@ extern "C" int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, i
                                 ldo, nullptr, as_stream(stream), out_lo);
   }
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
-  edge_apply_kernel<<<grid, block, 0, as_stream(stream)>>>(n, k, cout, PQ, ldpq, idx, scale, shift, out, ldo, out_lo);
+  caae::launch(edge_apply_kernel, grid, block, 0, as_stream(stream), n, k, cout, PQ, ldpq, idx, scale, shift, out, ldo, out_lo);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -731,7 +747,7 @@ extern "C" int caae_edge_bwd_reduce(int b, int n, int k, int cout, const float* 
                                 0, parts, as_stream(stream));
   }
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
-  edge_reduce_kernel<1><<<grid, block, 0, as_stream(stream)>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean, invstd,
+  caae::launch(edge_reduce_kernel<1>, grid, block, 0, as_stream(stream), n, k, cout, PQ, ldpq, idx, scale, shift, mean, invstd,
                                                                 dOut, lddo, parts);
   return CAAE_LAUNCH_STATUS();
 }
@@ -753,7 +769,7 @@ extern "C" int caae_edge_bwd_apply(int b, int n, int k, int cout, const float* P
                                     (size_t)b * n, s);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
-  edge_bwd_apply_kernel<<<grid, block, 0, s>>>(n, k, cout, PQ, ldpq, idx, scale, shift, mean, invstd, coef, dOut, lddo,
+  caae::launch(edge_bwd_apply_kernel, grid, block, 0, s, n, k, cout, PQ, ldpq, idx, scale, shift, mean, invstd, coef, dOut, lddo,
                                                dPQ, lddpq);
   return CAAE_LAUNCH_STATUS();
 }
@@ -768,11 +784,11 @@ extern "C" int caae_col_stats(int R, int C, const float* Y, int ld, double* part
   CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
   if (vec4_ok(C, Y, ld, nullptr, 0, nullptr, 0)) {
     grid.x = C / 128;
-    col_reduce_vec4_kernel<0><<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, nullptr, nullptr, nullptr, nullptr,
+    caae::launch(col_reduce_vec4_kernel<0>, grid, block, 0, as_stream(stream), R, C, Y, ld, nullptr, nullptr, nullptr, nullptr,
                                                                       nullptr, 0, 1, 1.f, 0, nullptr, parts);
     return CAAE_LAUNCH_STATUS();
   }
-  col_reduce_kernel<0><<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, nullptr, nullptr, nullptr, nullptr, nullptr,
+  caae::launch(col_reduce_kernel<0>, grid, block, 0, as_stream(stream), R, C, Y, ld, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                0, 1, 1.f, 0, nullptr, parts);
   return CAAE_LAUNCH_STATUS();
 }
@@ -783,7 +799,7 @@ extern "C" int caae_bn_finalize(int C, const double* parts, int nparts, double c
                                 caae_stream_t stream) {
   CAAE_RETURN_IF(C <= 0 || nparts <= 0 || count <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!parts || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd, CAAE_E_NULLPTR);
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, beta, ema_mean,
+  caae::launch(bn_finalize_kernel, (C + 31) / 32, dim3(32, 32), 0, as_stream(stream), C, parts, nparts, count, gamma, beta, ema_mean,
                                                                      ema_var, decay, scale, shift, save_mean,
                                                                      save_invstd);
   return CAAE_LAUNCH_STATUS();
@@ -793,7 +809,7 @@ extern "C" int caae_bn_eval_coeffs(int C, const float* gamma, const float* beta,
                                    const float* ema_var, float* scale, float* shift, caae_stream_t stream) {
   CAAE_RETURN_IF(C <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!gamma || !beta || !ema_mean || !ema_var || !scale || !shift, CAAE_E_NULLPTR);
-  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(C, gamma, beta, ema_mean, ema_var, scale, shift);
+  caae::launch(bn_eval_coeffs_kernel, (C + 127) / 128, 128, 0, as_stream(stream), C, gamma, beta, ema_mean, ema_var, scale, shift);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -802,7 +818,7 @@ extern "C" int caae_bn_bwd_finalize(int C, const double* parts, int nparts, doub
                                     caae_stream_t stream) {
   CAAE_RETURN_IF(C <= 0 || nparts <= 0 || count <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!parts || !gamma || !invstd || !coef || !dgamma || !dbeta, CAAE_E_NULLPTR);
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(C, parts, nparts, count, gamma, invstd, coef,
+  caae::launch(bn_bwd_finalize_kernel, (C + 31) / 32, dim3(32, 32), 0, as_stream(stream), C, parts, nparts, count, gamma, invstd, coef,
                                                                          dgamma, dbeta);
   return CAAE_LAUNCH_STATUS();
 }
@@ -812,7 +828,7 @@ extern "C" int caae_bn_act(int R, int C, const float* Y, int ld, const float* sc
   CAAE_RETURN_IF(R <= 0 || C <= 0 || ld < C || ldo < C, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!Y || !scale || !shift || !out, CAAE_E_NULLPTR);
   const long total = (long)R * C;
-  bn_act_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(total, C, Y, ld, scale, shift, relu, out, ldo);
+  caae::launch(bn_act_kernel, flat_blocks(total), 256, 0, as_stream(stream), total, C, Y, ld, scale, shift, relu, out, ldo);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -823,11 +839,11 @@ extern "C" int caae_bn_act_pool(int groups, int group, int C, const float* Y, in
   dim3 grid((C + 31) / 32, groups), block(32, 8);
   if (!maxpool && C % 128 == 0 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(emb) |
                                                    reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0) {
-    bn_act_meanpool_vec4_kernel<<<dim3(C / 128, groups), block, 0, as_stream(stream)>>>(group, C, Y, ld, scale, shift, emb);
+    caae::launch(bn_act_meanpool_vec4_kernel, dim3(C / 128, groups), block, 0, as_stream(stream), group, C, Y, ld, scale, shift, emb);
     return CAAE_LAUNCH_STATUS();
   }
-  if (maxpool) bn_act_pool_kernel<true><<<grid, block, 0, as_stream(stream)>>>(group, C, Y, ld, scale, shift, emb, argmax);
-  else bn_act_pool_kernel<false><<<grid, block, 0, as_stream(stream)>>>(group, C, Y, ld, scale, shift, emb, argmax);
+  if (maxpool) caae::launch(bn_act_pool_kernel<true>, grid, block, 0, as_stream(stream), group, C, Y, ld, scale, shift, emb, argmax);
+  else caae::launch(bn_act_pool_kernel<false>, grid, block, 0, as_stream(stream), group, C, Y, ld, scale, shift, emb, argmax);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -841,11 +857,11 @@ extern "C" int caae_bn_act_bwd_reduce(int R, int C, const float* Y, int ld, cons
   CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
   if (vec4_ok(C, Y, ld, dOut, lddo, nullptr, 0)) {
     grid.x = C / 128;
-    col_reduce_vec4_kernel<1><<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, scale, shift, mean, invstd, dOut,
+    caae::launch(col_reduce_vec4_kernel<1>, grid, block, 0, as_stream(stream), R, C, Y, ld, scale, shift, mean, invstd, dOut,
                                                                       lddo, group, gscale, relu, argmax, parts);
     return CAAE_LAUNCH_STATUS();
   }
-  col_reduce_kernel<1><<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, scale, shift, mean, invstd, dOut, lddo,
+  caae::launch(col_reduce_kernel<1>, grid, block, 0, as_stream(stream), R, C, Y, ld, scale, shift, mean, invstd, dOut, lddo,
                                                                group, gscale, relu, argmax, parts);
   return CAAE_LAUNCH_STATUS();
 }
@@ -859,12 +875,12 @@ extern "C" int caae_bn_act_bwd_apply(int R, int C, const float* Y, int ld, const
   if (vec4_ok(C, Y, ld, dOut, lddo, dY, lddy)) {
     dim3 grid(C / 128, (R + COL_ROWS - 1) / COL_ROWS), block(32, 8);
     CAAE_RETURN_IF(grid.y > 65535, CAAE_E_BADSHAPE);
-    bn_act_bwd_vec4_kernel<<<grid, block, 0, as_stream(stream)>>>(R, C, Y, ld, scale, shift, mean, invstd, coef, dOut,
+    caae::launch(bn_act_bwd_vec4_kernel, grid, block, 0, as_stream(stream), R, C, Y, ld, scale, shift, mean, invstd, coef, dOut,
                                                                    lddo, group, gscale, relu, argmax, dY, lddy);
     return CAAE_LAUNCH_STATUS();
   }
   const long total = (long)R * C;
-  bn_act_bwd_kernel<<<flat_blocks(total), 256, 0, as_stream(stream)>>>(total, C, Y, ld, scale, shift, mean, invstd,
+  caae::launch(bn_act_bwd_kernel, flat_blocks(total), 256, 0, as_stream(stream), total, C, Y, ld, scale, shift, mean, invstd,
                                                                        coef, dOut, lddo, group, gscale, relu, argmax,
                                                                        dY, lddy);
   return CAAE_LAUNCH_STATUS();
@@ -874,13 +890,13 @@ extern "C" int caae_edge_fold_weights(int c, int cout, const float* w, const flo
                                       int ldw, caae_stream_t stream) {
   CAAE_RETURN_IF(c <= 0 || cout <= 0 || ldw < cout, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!w || !wf || !bias_f, CAAE_E_NULLPTR);
-  edge_fold_weights_kernel<<<(c * cout + 255) / 256, 256, 0, as_stream(stream)>>>(c, cout, w, ldw, bias, wf, bias_f);
+  caae::launch(edge_fold_weights_kernel, (c * cout + 255) / 256, 256, 0, as_stream(stream), c, cout, w, ldw, bias, wf, bias_f);
   return CAAE_LAUNCH_STATUS();
 }
 
 extern "C" int caae_edge_unfold_wgrad(int c, int cout, const float* dwf, int lddwf, float* dw, caae_stream_t stream) {
   CAAE_RETURN_IF(c <= 0 || cout <= 0 || lddwf < 2 * cout, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!dwf || !dw, CAAE_E_NULLPTR);
-  edge_unfold_wgrad_kernel<<<(c * cout + 255) / 256, 256, 0, as_stream(stream)>>>(c, cout, dwf, lddwf, dw);
+  caae::launch(edge_unfold_wgrad_kernel, (c * cout + 255) / 256, 256, 0, as_stream(stream), c, cout, dwf, lddwf, dw);
   return CAAE_LAUNCH_STATUS();
 }

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(kNndThreads)
 nn_distance_fwd_kernel(int n, const float* __restrict__ xyz1, int m, const float* __restrict__ xyz2,
                        float* __restrict__ dist1, int* __restrict__ idx1, float* __restrict__ dist2,
                        int* __restrict__ idx2) {
+  pdl_wait();
   __shared__ __align__(16) float tile[kNndTile * 3];
 
   const int cloud = blockIdx.y;
@@ -121,6 +122,7 @@ nn_distance_bwd_smem_kernel(int n, const float* __restrict__ xyz1, int m, const 
                             const float* __restrict__ gd1, const int* __restrict__ idx1,
                             const float* __restrict__ gd2, const int* __restrict__ idx2,
                             float* __restrict__ gx1, float* __restrict__ gx2) {
+  pdl_wait();
   extern __shared__ float acc[];  // nA*3
   const int cloud = blockIdx.y;
   const bool first = (blockIdx.x == 0);
@@ -160,6 +162,7 @@ nn_distance_bwd_global_kernel(int n, const float* __restrict__ xyz1, int m, cons
                               const float* __restrict__ gd1, const int* __restrict__ idx1,
                               const float* __restrict__ gd2, const int* __restrict__ idx2,
                               float* __restrict__ gx1, float* __restrict__ gx2) {
+  pdl_wait();
   const int cloud = blockIdx.y;
   const bool first = (blockIdx.z == 0);
   const int nA = first ? n : m, nB = first ? m : n;
@@ -199,13 +202,13 @@ extern "C" int caae_nn_distance(int b, int n, const float* xyz, int m, const flo
   cudaStream_t s = as_stream(stream);
   if (ctas4 >= 2 * kNumSMs) {
     dim3 grid((big + 511) / 512, b, 2);
-    nn_distance_fwd_kernel<4><<<grid, kNndThreads, 0, s>>>(n, xyz, m, xyz2, result, result_i, result2, result2_i);
+    caae::launch(nn_distance_fwd_kernel<4>, grid, kNndThreads, 0, s, n, xyz, m, xyz2, result, result_i, result2, result2_i);
   } else if (ctas2 >= 2 * kNumSMs) {
     dim3 grid((big + 255) / 256, b, 2);
-    nn_distance_fwd_kernel<2><<<grid, kNndThreads, 0, s>>>(n, xyz, m, xyz2, result, result_i, result2, result2_i);
+    caae::launch(nn_distance_fwd_kernel<2>, grid, kNndThreads, 0, s, n, xyz, m, xyz2, result, result_i, result2, result2_i);
   } else {
     dim3 grid((big + 127) / 128, b, 2);
-    nn_distance_fwd_kernel<1><<<grid, kNndThreads, 0, s>>>(n, xyz, m, xyz2, result, result_i, result2, result2_i);
+    caae::launch(nn_distance_fwd_kernel<1>, grid, kNndThreads, 0, s, n, xyz, m, xyz2, result, result_i, result2, result2_i);
   }
   return CAAE_LAUNCH_STATUS();
 }
@@ -232,12 +235,12 @@ extern "C" int caae_nn_distance_grad(int b, int n, const float* xyz1, int m, con
                                            (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    nn_distance_bwd_smem_kernel<<<dim3(2, b), kNndBwdThreads, smem, s>>>(n, xyz1, m, xyz2, grad_dist1, idx1,
+    caae::launch(nn_distance_bwd_smem_kernel, dim3(2, b), kNndBwdThreads, smem, s, n, xyz1, m, xyz2, grad_dist1, idx1,
                                                                         grad_dist2, idx2, grad_xyz1, grad_xyz2);
   } else {
     cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * (size_t)b * n * 3, s);
     cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * (size_t)b * m * 3, s);
-    nn_distance_bwd_global_kernel<<<dim3((big + 255) / 256, b, 2), 256, 0, s>>>(
+    caae::launch(nn_distance_bwd_global_kernel, dim3((big + 255) / 256, b, 2), 256, 0, s, 
         n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2);
   }
   return CAAE_LAUNCH_STATUS();

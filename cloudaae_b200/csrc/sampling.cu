@@ -40,6 +40,7 @@ __device__ __forceinline__ void fps_block_argmax(uint32_t dbits, uint32_t prio, 
 template <int PPT>
 __global__ void __launch_bounds__(kFpsThreads)
 fps_reg_kernel(int n, int m, const float* __restrict__ inp, int* __restrict__ out, float* __restrict__ out_xyz) {
+  pdl_wait();
   extern __shared__ __align__(16) float s_xyz[];  // n*3: coordinate lookup of the last pick
   __shared__ uint2 s_red[2][kFpsWarps];
 
@@ -94,6 +95,7 @@ fps_reg_kernel(int n, int m, const float* __restrict__ inp, int* __restrict__ ou
 __global__ void __launch_bounds__(kFpsThreads)
 fps_generic_kernel(int n, int m, const float* __restrict__ inp, float* __restrict__ temp, int* __restrict__ out,
                    float* __restrict__ out_xyz) {
+  pdl_wait();
   __shared__ uint2 s_red[2][kFpsWarps];
   const int cloud = blockIdx.x, t = threadIdx.x;
   const float* __restrict__ pts = inp + (size_t)cloud * n * 3;
@@ -135,6 +137,7 @@ fps_generic_kernel(int n, int m, const float* __restrict__ inp, float* __restric
 __global__ void __launch_bounds__(256)
 gather_kernel(long total, int n, int m, const float* __restrict__ inp, const int* __restrict__ idx,
               float* __restrict__ out) {
+  pdl_wait();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const long p = e / 3;            // flat (cloud, j)
     const int c = (int)(e - p * 3);
@@ -146,6 +149,7 @@ gather_kernel(long total, int n, int m, const float* __restrict__ inp, const int
 __global__ void __launch_bounds__(256)
 scatter_add_kernel(long total, int n, int m, const float* __restrict__ out_g, const int* __restrict__ idx,
                    float* __restrict__ inp_g) {
+  pdl_wait();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const long p = e / 3;
     const int c = (int)(e - p * 3);
@@ -176,6 +180,7 @@ __device__ __forceinline__ bool scan_down_target(int pos1, int w) {   // pos1 = 
 __global__ void __launch_bounds__(kScanThreads)
 prob_sample_kernel(int n, int m, const float* __restrict__ inp_p, const float* __restrict__ inp_r,
                    float* __restrict__ temp, int* __restrict__ out) {
+  pdl_wait();
   __shared__ float warp_total[kScanThreads / 32], warp_prefix[kScanThreads / 32], chunk_total;
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* __restrict__ src = inp_p + (size_t)row * n;
@@ -283,7 +288,7 @@ static int launch_fps_reg(int b, int n, int m, const float* inp, int* out, float
     cudaError_t e = cudaFuncSetAttribute(fps_reg_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  fps_reg_kernel<PPT><<<b, kFpsThreads, smem, s>>>(n, m, inp, out, out_xyz);
+  caae::launch(fps_reg_kernel<PPT>, b, kFpsThreads, smem, s, n, m, inp, out, out_xyz);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -314,7 +319,7 @@ extern "C" int caae_fps_gather(int b, int n, int m, const float* inp, float* tem
   if (ppt <= 12) return launch_fps_reg<12>(b, n, m, inp, out, out_xyz, s);
   if (ppt <= 16) return launch_fps_reg<16>(b, n, m, inp, out, out_xyz, s);
   CAAE_RETURN_IF(!temp, CAAE_E_SCRATCH);
-  fps_generic_kernel<<<b, kFpsThreads, 0, s>>>(n, m, inp, temp, out, out_xyz);
+  caae::launch(fps_generic_kernel, b, kFpsThreads, 0, s, n, m, inp, temp, out, out_xyz);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -334,7 +339,7 @@ extern "C" int caae_gather(int b, int n, int m, const float* inp, const int* idx
   CAAE_RETURN_IF(n == 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!inp || !idx || !out, CAAE_E_NULLPTR);
   const long total = (long)b * m * 3;
-  gather_kernel<<<flat_grid(total), 256, 0, as_stream(stream)>>>(total, n, m, inp, idx, out);
+  caae::launch(gather_kernel, flat_grid(total), 256, 0, as_stream(stream), total, n, m, inp, idx, out);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -349,7 +354,7 @@ extern "C" int caae_gather_grad(int b, int n, int m, const float* out_g, const i
   if (m == 0) return CAAE_OK;
   CAAE_RETURN_IF(!out_g || !idx, CAAE_E_NULLPTR);
   const long total = (long)b * m * 3;
-  scatter_add_kernel<<<flat_grid(total), 256, 0, s>>>(total, n, m, out_g, idx, inp_g);
+  caae::launch(scatter_add_kernel, flat_grid(total), 256, 0, s, total, n, m, out_g, idx, inp_g);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -360,6 +365,6 @@ extern "C" int caae_prob_sample(int b, int n, int m, const float* inp_p, const f
   CAAE_RETURN_IF(n == 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!inp_p || !inp_r || !out, CAAE_E_NULLPTR);
   CAAE_RETURN_IF(!temp, CAAE_E_SCRATCH);
-  prob_sample_kernel<<<b, kScanThreads, 0, as_stream(stream)>>>(n, m, inp_p, inp_r, temp, out);
+  caae::launch(prob_sample_kernel, b, kScanThreads, 0, as_stream(stream), n, m, inp_p, inp_r, temp, out);
   return CAAE_LAUNCH_STATUS();
 }

@@ -78,6 +78,7 @@ __global__ void pose_loss_kernel(int b, const float* __restrict__ rot_pred, cons
                                  double* __restrict__ per_rot, float* __restrict__ per_trans,
                                  float* __restrict__ d_rot, float* __restrict__ d_trans,
                                  float* __restrict__ trans_pred_out) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b) return;
   // ---- rotation (float64)
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(1024)
 loss_reduce_kernel(long npt, const float* __restrict__ dist1, const float* __restrict__ dist2, int b,
                    const float* __restrict__ per_trans, const double* __restrict__ per_rot,
                    float* __restrict__ losses) {
+  pdl_wait();
   __shared__ double s_red[3][32];
   double c = 0.0, t = 0.0, r = 0.0;
   for (long e = threadIdx.x; e < npt; e += 1024) c += (double)(dist1[e] + dist2[e]);
@@ -142,6 +144,7 @@ loss_reduce_kernel(long npt, const float* __restrict__ dist1, const float* __res
 // out[b,p,:] = in[b,p,:] + v[b,:]
 __global__ void add_cloud_vec_kernel(long total, int npts, const float* __restrict__ in, const float* __restrict__ v,
                                      float* __restrict__ out) {
+  pdl_wait();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const long cloud = e / (3L * npts);
     out[e] = in[e] + v[cloud * 3 + (e % 3)];
@@ -152,6 +155,7 @@ __global__ void add_cloud_vec_kernel(long total, int npts, const float* __restri
 __global__ void __launch_bounds__(256)
 prepare_input_kernel(int npoint, int vis_stride_pts, const float* __restrict__ visible, const float* __restrict__ noise,
                      const int* __restrict__ class_id, int nclass, float* __restrict__ x, float* __restrict__ mean_out) {
+  pdl_wait();
   __shared__ float s_sum[3][8];
   __shared__ float s_mean[3];
   const int cloud = blockIdx.x, tid = threadIdx.x;
@@ -186,6 +190,7 @@ prepare_input_kernel(int npoint, int vis_stride_pts, const float* __restrict__ v
 
 // state = {int step, int adam_t, float bn_decay}: called once at the start of every training step
 __global__ void step_begin_kernel(int* __restrict__ state, int batch_size) {
+  pdl_wait();
   const int step = state[0];
   const double mom = 0.5 * pow(0.5, floor((double)step * (double)batch_size / 40.0));
   float decay = (float)(1.0 - mom);
@@ -197,6 +202,7 @@ __global__ void step_begin_kernel(int* __restrict__ state, int batch_size) {
 __global__ void __launch_bounds__(256)
 adam_tf_kernel(long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                const int* __restrict__ state, float lr, float beta1, float beta2, float eps, float grad_scale) {
+  pdl_wait();
   __shared__ float s_lr;
   if (threadIdx.x == 0) {
     const double t = (double)state[1];
@@ -234,6 +240,7 @@ adam_tf_kernel(long n, float* __restrict__ p, const float* __restrict__ g, float
 }
 
 __global__ void fill_kernel(long n, float* __restrict__ p, float value) {
+  pdl_wait();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = value;
 }
 
@@ -255,7 +262,7 @@ extern "C" int caae_pose_losses(int b, const float* rot_pred, const float* axag_
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!rot_pred || !axag_label || !trans_res || !mean || !trans_label || !per_rot || !per_trans || !d_rot ||
                  !d_trans, CAAE_E_NULLPTR);
-  pose_loss_kernel<<<(b + 63) / 64, 64, 0, as_stream(stream)>>>(b, rot_pred, axag_label, trans_res, mean, trans_label,
+  caae::launch(pose_loss_kernel, (b + 63) / 64, 64, 0, as_stream(stream), b, rot_pred, axag_label, trans_res, mean, trans_label,
                                                                 w_rot, w_trans, per_rot, per_trans, d_rot, d_trans,
                                                                 trans_pred);
   return CAAE_LAUNCH_STATUS();
@@ -265,7 +272,7 @@ extern "C" int caae_loss_reduce(long npt, const float* dist1, const float* dist2
                                 const double* per_rot, float* losses, caae_stream_t stream) {
   CAAE_RETURN_IF(npt <= 0 || b <= 0, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!dist1 || !dist2 || !per_trans || !per_rot || !losses, CAAE_E_NULLPTR);
-  loss_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(npt, dist1, dist2, b, per_trans, per_rot, losses);
+  caae::launch(loss_reduce_kernel, 1, 1024, 0, as_stream(stream), npt, dist1, dist2, b, per_trans, per_rot, losses);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -274,7 +281,7 @@ extern "C" int caae_add_cloud_vec(int b, int npts, const float* in, const float*
   if (b == 0 || npts == 0) return CAAE_OK;
   CAAE_RETURN_IF(!in || !v || !out, CAAE_E_NULLPTR);
   const long total = (long)b * npts * 3;
-  add_cloud_vec_kernel<<<flat_blocks2(total), 256, 0, as_stream(stream)>>>(total, npts, in, v, out);
+  caae::launch(add_cloud_vec_kernel, flat_blocks2(total), 256, 0, as_stream(stream), total, npts, in, v, out);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -283,14 +290,14 @@ extern "C" int caae_prepare_input(int b, int npoint, int vis_stride_pts, const f
   CAAE_RETURN_IF(b < 0 || npoint <= 0 || vis_stride_pts < npoint || nclass < 0, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!visible || !class_id || !x || !mean_out, CAAE_E_NULLPTR);
-  prepare_input_kernel<<<b, 256, 0, as_stream(stream)>>>(npoint, vis_stride_pts, visible, noise, class_id, nclass, x,
+  caae::launch(prepare_input_kernel, b, 256, 0, as_stream(stream), npoint, vis_stride_pts, visible, noise, class_id, nclass, x,
                                                         mean_out);
   return CAAE_LAUNCH_STATUS();
 }
 
 extern "C" int caae_step_begin(int* state, int batch_size, caae_stream_t stream) {
   CAAE_RETURN_IF(!state, CAAE_E_NULLPTR);
-  step_begin_kernel<<<1, 1, 0, as_stream(stream)>>>(state, batch_size);
+  caae::launch(step_begin_kernel, 1, 1, 0, as_stream(stream), state, batch_size);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -299,7 +306,7 @@ extern "C" int caae_adam_tf(long n, float* p, const float* g, float* m, float* v
   CAAE_RETURN_IF(n < 0, CAAE_E_BADSHAPE);
   if (n == 0) return CAAE_OK;
   CAAE_RETURN_IF(!p || !g || !m || !v || !state, CAAE_E_NULLPTR);
-  adam_tf_kernel<<<flat_blocks2(n), 256, 0, as_stream(stream)>>>(n, p, g, m, v, state, lr, beta1, beta2, eps,
+  caae::launch(adam_tf_kernel, flat_blocks2(n), 256, 0, as_stream(stream), n, p, g, m, v, state, lr, beta1, beta2, eps,
                                                                 grad_scale);
   return CAAE_LAUNCH_STATUS();
 }
@@ -308,6 +315,6 @@ extern "C" int caae_fill_f32(long n, float* p, float value, caae_stream_t stream
   CAAE_RETURN_IF(n < 0, CAAE_E_BADSHAPE);
   if (n == 0) return CAAE_OK;
   CAAE_RETURN_IF(!p, CAAE_E_NULLPTR);
-  fill_kernel<<<flat_blocks2(n), 256, 0, as_stream(stream)>>>(n, p, value);
+  caae::launch(fill_kernel, flat_blocks2(n), 256, 0, as_stream(stream), n, p, value);
   return CAAE_LAUNCH_STATUS();
 }

@@ -225,6 +225,7 @@ class _Engine:
         self.x0 = None
         self.trained = (False, False)
         self.after_fc_backward = None
+        self.after_last_conv_wgrad = None
         # Independent kernel chains run on forked side streams (and become parallel branches of the
         # captured CUDA graph): the three FC branches, weight gradients next to the data-gradient chain,
         # the EdgeConv projection next to the kNN search of the same layer.  Every launch of those chains
@@ -635,6 +636,8 @@ class _Engine:
             if se is not None: self._fork(se)
             with self._on(se):
                 self._dense_wgrad(scope, self.hcat, 320, R, self.yagg, False)
+                if self.after_last_conv_wgrad is not None:   # dgcnn_agg's gradients are final: start their allreduce
+                    self.after_last_conv_wgrad()
             self._gemm(0, 1, R, 320, 1024, self.yagg, 1024, self.v[f"{scope}/weights"], 1024, self.d_hcat, 320)
             for l in (3, 2, 1, 0):
                 scope = f"dgcnn{l + 1}"
@@ -670,6 +673,8 @@ class _Engine:
                 fin, fout, _ = self.scopes[scope]
                 inp, ldi = (self.x0, self.D) if i == 0 else (self.enc_a[i - 1], fin)
                 self._dense_wgrad(scope, inp, ldi, R, d_y, False)
+                if i == last and self.after_last_conv_wgrad is not None:
+                    self.after_last_conv_wgrad()
                 if i > 0:
                     self._gemm(0, 1, R, fin, fout, d_y, fout, self.v[f"{scope}/weights"], fout, self.enc_d[i - 1], fin)
                     prev = self.enc[i - 1]

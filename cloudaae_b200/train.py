@@ -64,13 +64,17 @@ class CloudAAETrainer:
         self._graph = None
         self._static = None
         self.launches_per_step = 0
-        # gradient exchange: bucket 1 = everything after the encoder (FC decoder + pose heads), complete
-        # as soon as the FC backward has run; bucket 0 = the encoder, complete at the end of backward.
+        # gradient exchange in three buckets, each started the moment its gradients are final: 2 = everything after the
+        # encoder (FC decoder + pose heads, 94 % of the bytes: after the FC backward), 1 = the last encoder convolution
+        # (dgcnn_agg / pn_conv5, 1.3 MB: right after its weight gradient, at the START of the encoder backward), 0 = the
+        # first four encoder layers (0.1 MB: at the end of backward — the only exchange left exposed in front of Adam).
         enc_last = "dgcnn_agg" if model == "dgcnn" else "pn_conv5_encoder"
+        first = self.v.index[f"{enc_last}/weights"][0]
         split = self.v.index[f"{enc_last}/bn/gamma"][0] + 1024
         split = ((split + 31) // 32) * 32
-        self.reducer = BucketedAllReduce(self.v.grad, [0, split, self.v.grad.numel()], group=process_group)
-        self.engine.after_fc_backward = (lambda: self.reducer.start(1)) if self.world > 1 else None
+        self.reducer = BucketedAllReduce(self.v.grad, [0, first, split, self.v.grad.numel()], group=process_group)
+        self.engine.after_fc_backward = (lambda: self.reducer.start(2)) if self.world > 1 else None
+        self.engine.after_last_conv_wgrad = (lambda: self.reducer.start(1)) if self.world > 1 else None
         if self.world > 1:
             broadcast_variables(self.v.flat, self.v.ema, group=process_group)
 
