@@ -61,7 +61,8 @@ _SIGNATURES = {
     "caae_bn_eval_coeffs": "ippppp" "pp",
     "caae_bn_bwd_finalize": "ipidppppp" "p",
     "caae_bn_act": "iipippipi" "p",
-    "caae_bn_act_pool": "iiipippipp" "p",
+    "caae_bn_act_pool": "iiipippipppp" "p",
+    "caae_bn_pool_bwd_finalize": "iiipifpppppppp" "p",
     "caae_bn_act_bwd_reduce": "iipipppppiifipp" "p",
     "caae_bn_act_bwd_apply": "iipippppppiifippi" "p",
     "caae_colsum": "iipip" "p",

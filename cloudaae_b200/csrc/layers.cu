@@ -335,9 +335,12 @@ bn_act_pool_kernel(int group, int C, const float* __restrict__ Y, int ld, const 
 // four independent 16-byte loads in flight per thread
 __global__ void __launch_bounds__(256)
 bn_act_meanpool_vec4_kernel(int group, int C, const float* __restrict__ Y, int ld, const float* __restrict__ scale,
-                            const float* __restrict__ shift, float* __restrict__ emb) {
+                            const float* __restrict__ shift, float* __restrict__ emb, float* __restrict__ pos_cnt,
+                            float* __restrict__ pos_sum) {
   pdl_wait();
   __shared__ float4 s_v[8][32];
+  __shared__ float4 s_c[8][32], s_y[8][32];
+  float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f), ysum = make_float4(0.f, 0.f, 0.f, 0.f);
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * 128 + tx * 4, g = blockIdx.y;
   const float4 sc = *reinterpret_cast<const float4*>(scale + ch), sh = *reinterpret_cast<const float4*>(shift + ch);
@@ -351,17 +354,72 @@ bn_act_meanpool_vec4_kernel(int group, int C, const float* __restrict__ Y, int l
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (r + 8 * u >= group) break;
-      acc.x += fmaxf(fmaf(y[u].x, sc.x, sh.x), 0.f); acc.y += fmaxf(fmaf(y[u].y, sc.y, sh.y), 0.f);
-      acc.z += fmaxf(fmaf(y[u].z, sc.z, sh.z), 0.f); acc.w += fmaxf(fmaf(y[u].w, sc.w, sh.w), 0.f);
+      const float a0 = fmaf(y[u].x, sc.x, sh.x), a1 = fmaf(y[u].y, sc.y, sh.y), a2 = fmaf(y[u].z, sc.z, sh.z), a3 = fmaf(y[u].w, sc.w, sh.w);
+      acc.x += fmaxf(a0, 0.f); acc.y += fmaxf(a1, 0.f); acc.z += fmaxf(a2, 0.f); acc.w += fmaxf(a3, 0.f);
+      if (pos_cnt != nullptr) {   // what the backward pass needs of the ReLU mask: per (cloud, channel) count and sum of y over the positive rows
+        if (a0 > 0.f) { cnt.x += 1.f; ysum.x += y[u].x; }
+        if (a1 > 0.f) { cnt.y += 1.f; ysum.y += y[u].y; }
+        if (a2 > 0.f) { cnt.z += 1.f; ysum.z += y[u].z; }
+        if (a3 > 0.f) { cnt.w += 1.f; ysum.w += y[u].w; }
+      }
     }
   }
   s_v[ty][tx] = acc;
+  if (pos_cnt != nullptr) { s_c[ty][tx] = cnt; s_y[ty][tx] = ysum; }
   __syncthreads();
   if (ty == 0) {
 #pragma unroll
     for (int r = 1; r < 8; ++r) { const float4 o = s_v[r][tx]; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
     const float inv = 1.f / (float)group;
     *reinterpret_cast<float4*>(emb + (size_t)g * C + ch) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    if (pos_cnt != nullptr) {
+#pragma unroll
+      for (int r = 1; r < 8; ++r) {
+        const float4 o = s_c[r][tx], q = s_y[r][tx];
+        cnt.x += o.x; cnt.y += o.y; cnt.z += o.z; cnt.w += o.w; ysum.x += q.x; ysum.y += q.y; ysum.z += q.z; ysum.w += q.w;
+      }
+      *reinterpret_cast<float4*>(pos_cnt + (size_t)g * C + ch) = cnt;
+      *reinterpret_cast<float4*>(pos_sum + (size_t)g * C + ch) = ysum;
+    }
+  }
+}
+
+// Backward statistics of mean-pool + ReLU + training-mode BN WITHOUT a pass over the [R, C] pre-activation: with
+// dy[r][c] = relu'(..) * d_emb[g(r)][c] / group the two sums the BN backward needs collapse to per-(cloud, channel) terms,
+//   sum_r dy = sum_g d_g * cnt[g][c],   sum_r dy * yhat = sum_g d_g * (pos_sum[g][c] - cnt[g][c] * mean[c]) * invstd[c],
+// where cnt / pos_sum were written by the forward pool pass.  coef = [mean(dy) | mean(dy*yhat) | gamma*invstd] as
+// bn_bwd_finalize_kernel produces it.  block (32 channels, 32 group lanes).
+__global__ void __launch_bounds__(1024)
+bn_pool_bwd_finalize_kernel(int C, int groups, double count, const float* __restrict__ d_emb, int ldd, float gscale,
+                            const float* __restrict__ pos_cnt, const float* __restrict__ pos_sum,
+                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                            const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
+                            float* __restrict__ dbeta) {
+  pdl_wait();
+  __shared__ double r_a[32][33], r_b[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * 32 + tx;
+  double a = 0.0, b = 0.0;
+  if (ch < C) {
+    const double mu = (double)mean[ch], is = (double)invstd[ch];
+    for (int g = ty; g < groups; g += 32) {
+      const double d = (double)(d_emb[(size_t)g * ldd + ch] * gscale);
+      const double c = (double)pos_cnt[(size_t)g * C + ch];
+      a += d * c;
+      b += d * (((double)pos_sum[(size_t)g * C + ch] - c * mu) * is);
+    }
+  }
+  r_a[ty][tx] = a; r_b[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && ch < C) {
+    double s = 0.0, ss = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) { s += r_a[r][tx]; ss += r_b[r][tx]; }
+    coef[ch] = (float)(s / count);
+    coef[C + ch] = (float)(ss / count);
+    coef[2 * C + ch] = gamma[ch] * invstd[ch];
+    dgamma[ch] = (float)ss;
+    dbeta[ch] = (float)s;
   }
 }
 
@@ -832,16 +890,32 @@ extern "C" int caae_bn_act(int R, int C, const float* Y, int ld, const float* sc
   return CAAE_LAUNCH_STATUS();
 }
 
+extern "C" int caae_bn_pool_bwd_finalize(int C, int groups, int group, const float* d_emb, int ldd, float gscale,
+                                         const float* pos_cnt, const float* pos_sum, const float* mean,
+                                         const float* invstd, const float* gamma, float* coef, float* dgamma,
+                                         float* dbeta, caae_stream_t stream) {
+  CAAE_RETURN_IF(C <= 0 || groups <= 0 || group <= 0 || ldd < C, CAAE_E_BADSHAPE);
+  CAAE_RETURN_IF(!d_emb || !pos_cnt || !pos_sum || !mean || !invstd || !gamma || !coef || !dgamma || !dbeta, CAAE_E_NULLPTR);
+  caae::launch(bn_pool_bwd_finalize_kernel, (C + 31) / 32, dim3(32, 32), 0, as_stream(stream), C, groups,
+               (double)groups * (double)group, d_emb, ldd, gscale, pos_cnt, pos_sum, mean, invstd, gamma, coef, dgamma, dbeta);
+  return CAAE_LAUNCH_STATUS();
+}
+
 extern "C" int caae_bn_act_pool(int groups, int group, int C, const float* Y, int ld, const float* scale,
-                                const float* shift, int maxpool, float* emb, int* argmax, caae_stream_t stream) {
+                                const float* shift, int maxpool, float* emb, int* argmax, float* pos_cnt, float* pos_sum,
+                                caae_stream_t stream) {
   CAAE_RETURN_IF(groups <= 0 || group <= 0 || C <= 0 || ld < C || groups > 65535, CAAE_E_BADSHAPE);
   CAAE_RETURN_IF(!Y || !scale || !shift || !emb, CAAE_E_NULLPTR);
   dim3 grid((C + 31) / 32, groups), block(32, 8);
   if (!maxpool && C % 128 == 0 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(emb) |
                                                    reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0) {
-    caae::launch(bn_act_meanpool_vec4_kernel, dim3(C / 128, groups), block, 0, as_stream(stream), group, C, Y, ld, scale, shift, emb);
+    CAAE_RETURN_IF((pos_cnt == nullptr) != (pos_sum == nullptr), CAAE_E_NULLPTR);
+    CAAE_RETURN_IF(pos_cnt && ((reinterpret_cast<uintptr_t>(pos_cnt) | reinterpret_cast<uintptr_t>(pos_sum)) & 15), CAAE_E_UNSUPPORTED);
+    caae::launch(bn_act_meanpool_vec4_kernel, dim3(C / 128, groups), block, 0, as_stream(stream), group, C, Y, ld, scale, shift, emb,
+                 pos_cnt, pos_sum);
     return CAAE_LAUNCH_STATUS();
   }
+  CAAE_RETURN_IF(pos_cnt != nullptr || pos_sum != nullptr, CAAE_E_UNSUPPORTED);   // only the float4 mean-pool kernel records them
   if (maxpool) caae::launch(bn_act_pool_kernel<true>, grid, block, 0, as_stream(stream), group, C, Y, ld, scale, shift, emb, argmax);
   else caae::launch(bn_act_pool_kernel<false>, grid, block, 0, as_stream(stream), group, C, Y, ld, scale, shift, emb, argmax);
   return CAAE_LAUNCH_STATUS();

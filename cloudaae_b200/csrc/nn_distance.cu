@@ -144,13 +144,48 @@ nn_distance_bwd_smem_kernel(int n, const float* __restrict__ xyz1, int m, const 
       acc[j * 3 + c] = __fmul_rn(__fsub_rn(A[j * 3 + c], B[j2 * 3 + c]), g);
   }
   __syncthreads();
-  // cross terms: -(g*(b_j - a_{idxB[j]})) lands on a_{idxB[j]}
-  for (int j = threadIdx.x; j < nB; j += kNndBwdThreads) {
-    const int j2 = idxB[j];
-    const float g = __fadd_rn(gdB[j], gdB[j]);
+  // cross terms: -(g*(b_j - a_{idxB[j]})) lands on a_{idxB[j]}.  Shared-memory float atomics are compare-and-swap
+  // loops, and an untrained decoder sends all 1024 reconstructed points to the same two or three targets: 1024-way
+  // contention on three words (48 us at b = 128, against 12 us on spread clouds).  So a warp first combines the
+  // lanes that hit the same target (match_any + a shuffle tree over each group) and only group leaders touch memory;
+  // warps whose 32 targets are all different skip straight to the atomics.
+  const int nB_pad = (nB + 31) & ~31;
+  for (int j = threadIdx.x; j < nB_pad; j += kNndBwdThreads) {
+    const bool live = j < nB;
+    const int j2 = live ? idxB[j] : -1 - (int)(threadIdx.x & 31);     // dead lanes: unique keys, zero values
+    const float g = live ? __fadd_rn(gdB[j], gdB[j]) : 0.f;
+    float v[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      atomicAdd(&acc[j2 * 3 + c], -__fmul_rn(__fsub_rn(B[j * 3 + c], A[j2 * 3 + c]), g));
+    for (int c = 0; c < 3; ++c) v[c] = live ? -__fmul_rn(__fsub_rn(B[j * 3 + c], A[j2 * 3 + c]), g) : 0.f;
+    const unsigned peers = __match_any_sync(0xffffffffu, j2);
+    if (__all_sync(0xffffffffu, peers == (1u << (threadIdx.x & 31)))) {
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(&acc[j2 * 3 + c], v[c]);
+      }
+      continue;
+    }
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    // group sum: every lane walks the other members of ITS group in ascending lane order (fixed order per group)
+    float s[3] = {v[0], v[1], v[2]};
+    unsigned rest = peers & ~(1u << leader);
+    // (warp-uniform trip count: the largest group)
+    int trips = __popc(rest);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));
+    for (int t = 0; t < trips; ++t) {
+      const int src = rest ? __ffs(rest) - 1 : lane;
+      rest &= rest - 1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float o = __shfl_sync(0xffffffffu, v[c], src);
+        if (lane == leader && src != lane) s[c] += o;
+      }
+    }
+    if (live && lane == leader) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) atomicAdd(&acc[j2 * 3 + c], s[c]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nA * 3; i += kNndBwdThreads) out[i] = acc[i];

@@ -183,6 +183,8 @@ class _Engine:
             self.bf = [torch.empty(2 * co, **f32) for co in self.couts]
             self.d_wf = [torch.empty(ci, 2 * co, **f32) for ci, co in zip(self.cins, self.couts)]
             self.yagg = torch.empty(R, 1024, **f32)
+            self.pos_cnt = torch.empty(B, 1024, **f32)   # ReLU-mask statistics of the pooled layer (forward -> BN backward)
+            self.pos_sum = torch.empty(B, 1024, **f32)
         else:
             self.enc = ["pn_conv1_encoder", "pn_conv2_encoder", "pn_conv3_encoder", "pn_conv4_encoder",
                         "pn_conv5_encoder"]
@@ -563,7 +565,8 @@ class _Engine:
                 self._dense_fwd(scope, self.hcat, 320, R, train_enc, decay, self.yagg, None,
                                 x_lo=self.hcat_lo if self.x3 else None)
                 self._c("caae_bn_act_pool", B, N, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]),
-                        self._p(bn["shift"]), 0, self._p(self.emb), None)
+                        self._p(bn["shift"]), 0, self._p(self.emb), None,
+                        self._p(self.pos_cnt if train_enc else None), self._p(self.pos_sum if train_enc else None))
             if want_before_embedding:
                 before = torch.empty(R, 1024, dtype=torch.float32, device=self.dev)
                 self._c("caae_bn_act", R, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]), self._p(bn["shift"]),
@@ -586,7 +589,7 @@ class _Engine:
             if not pooled:
                 bn = self.bn[self.enc[-1]]
                 self._c("caae_bn_act_pool", B, N, 1024, self._p(self.enc_y[-1]), 1024, self._p(bn["scale"]),
-                        self._p(bn["shift"]), 1, self._p(self.emb), self._p(self.argmax))
+                        self._p(bn["shift"]), 1, self._p(self.emb), self._p(self.argmax), None, None)
         if se is not None: self._join(se)
         self.forward_fc(train_fc, decay)
         outs = [self.fc_y[br[-1]] for br in self.branches]
@@ -630,8 +633,15 @@ class _Engine:
         B, N, R, k = self.B, self.N, self.R, self.k
         if self.model == "dgcnn":
             scope = "dgcnn_agg"
-            # mean-pool + ReLU + BN backward, in place over the pre-activation
-            self._bn_bwd(scope, R, self.yagg, self.d_emb, 1024, N, 1.0 / N, None, self.yagg)
+            # mean-pool + ReLU + BN backward, in place over the pre-activation.  The two reductions over the 134 MB
+            # pre-activation collapse to per-(cloud, channel) terms the forward pool pass recorded.
+            bn, v = self.bn[scope], self.v
+            self._c("caae_bn_pool_bwd_finalize", 1024, B, N, self._p(self.d_emb), 1024, 1.0 / N, self._p(self.pos_cnt),
+                    self._p(self.pos_sum), self._p(bn["mean"]), self._p(bn["invstd"]), self._p(v[f"{scope}/bn/gamma"]),
+                    self._p(bn["coef"]), self._p(v.grad_of(f"{scope}/bn/gamma")), self._p(v.grad_of(f"{scope}/bn/beta")))
+            self._c("caae_bn_act_bwd_apply", R, 1024, self._p(self.yagg), 1024, self._p(bn["scale"]), self._p(bn["shift"]),
+                    self._p(bn["mean"]), self._p(bn["invstd"]), self._p(bn["coef"]), self._p(self.d_emb), 1024, N,
+                    1.0 / N, 1, None, self._p(self.yagg), 1024)
             se = self.s_enc   # weight gradients next to the data-gradient chain
             if se is not None: self._fork(se)
             with self._on(se):

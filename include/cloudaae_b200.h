@@ -178,7 +178,14 @@ int caae_bn_bwd_finalize(int C, const double* parts, int nparts, double count, c
 int caae_bn_act(int R, int C, const float* Y, int ld, const float* scale, const float* shift, int relu, float* out,
                 int ldo, caae_stream_t stream);
 int caae_bn_act_pool(int groups, int group, int C, const float* Y, int ld, const float* scale, const float* shift,
-                     int maxpool, float* emb, int* argmax, caae_stream_t stream);
+                     int maxpool, float* emb, int* argmax, float* pos_cnt, float* pos_sum, caae_stream_t stream);
+/* Mean pool in training mode: pos_cnt / pos_sum f32[groups, C] (both or neither; NULL = not recorded) receive, per cloud
+ * and channel, the number of rows whose ReLU is open and the sum of y over them.  caae_bn_pool_bwd_finalize turns them
+ * and d(embedding) into the batch-norm backward coefficients (coef f32[3C], dgamma, dbeta as caae_bn_bwd_finalize) — the
+ * statistics pass over the [groups*group, C] pre-activation (caae_bn_act_bwd_reduce) is not needed. */
+int caae_bn_pool_bwd_finalize(int C, int groups, int group, const float* d_emb, int ldd, float gscale, const float* pos_cnt,
+                              const float* pos_sum, const float* mean, const float* invstd, const float* gamma, float* coef,
+                              float* dgamma, float* dbeta, caae_stream_t stream);
 int caae_bn_act_bwd_reduce(int R, int C, const float* Y, int ld, const float* scale, const float* shift,
                            const float* mean, const float* invstd, const float* dOut, int lddo, int group,
                            float gscale, int relu, const int* argmax, double* parts, caae_stream_t stream);

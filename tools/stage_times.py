@@ -129,8 +129,12 @@ def measure(tr, syn, c, ax, tl, iters=30, detail=True):
             ("L1 knn (xyz, all-pairs part)", lambda: eng._c("caae_knn_part", 2, p(eng.knn_flags), B, N, 3, k, p(tr.x), eng.D, p(eng.idx[0]))),
             ("knn classify", lambda: eng._c("caae_knn_classify", B, N, eng.D, p(tr.x), eng.D, p(eng.knn_flags))),
             ("agg gemm fwd (+stats)", lambda: eng._dense_fwd("dgcnn_agg", eng.hcat, 320, R, True, tr.decay, eng.yagg, None, x_lo=eng.hcat_lo if eng.x3 else None)),
-            ("agg bn_act_pool", lambda: eng._c("caae_bn_act_pool", B, N, 1024, p(eng.yagg), 1024, p(bn["scale"]), p(bn["shift"]), 0, p(eng.emb), None)),
-            ("agg bn_bwd (3 launches)", lambda: eng._bn_bwd("dgcnn_agg", R, eng.yagg, eng.d_emb, 1024, N, 1.0 / N, None, eng.yagg)),
+            ("agg bn_act_pool", lambda: eng._c("caae_bn_act_pool", B, N, 1024, p(eng.yagg), 1024, p(bn["scale"]), p(bn["shift"]), 0, p(eng.emb), None, p(eng.pos_cnt), p(eng.pos_sum))),
+            ("agg bn_bwd (finalize + apply)", lambda: (
+                eng._c("caae_bn_pool_bwd_finalize", 1024, B, N, p(eng.d_emb), 1024, 1.0 / N, p(eng.pos_cnt), p(eng.pos_sum), p(bn["mean"]), p(bn["invstd"]),
+                       p(tr.v["dgcnn_agg/bn/gamma"]), p(bn["coef"]), p(tr.v.grad_of("dgcnn_agg/bn/gamma")), p(tr.v.grad_of("dgcnn_agg/bn/beta"))),
+                eng._c("caae_bn_act_bwd_apply", R, 1024, p(eng.yagg), 1024, p(bn["scale"]), p(bn["shift"]), p(bn["mean"]), p(bn["invstd"]), p(bn["coef"]),
+                       p(eng.d_emb), 1024, N, 1.0 / N, 1, None, p(eng.yagg), 1024))),
             ("agg wgrad gemm", lambda: eng._dense_wgrad("dgcnn_agg", eng.hcat, 320, R, eng.yagg, False)),
             ("agg dgrad gemm", lambda: eng._gemm(0, 1, R, 320, 1024, eng.yagg, 1024, W, 1024, eng.d_hcat, 320)),
             ("nn_distance fwd", lambda: tr._c("caae_nn_distance", B, M, p(tr.recon), M, p(tgt), p(tr.dist1), p(tr.idx1), p(tr.dist2), p(tr.idx2))),
