@@ -54,6 +54,8 @@ _SIGNATURES = {
     "caae_knn_part": "ipiiiipip" "p",
     "caae_edge_stats": "iiiipipp" "p",
     "caae_edge_apply": "iiiipippppip" "p",
+    "caae_edge_apply_fused": "iiiipippid" "pppppppppp" "ip" "p",
+    "caae_edge_bwd_apply_fused": "iiiipip" "ppppp" "id" "pppp" "pipi" "p",
     "caae_edge_bwd_reduce": "iiiipippppppip" "p",
     "caae_edge_bwd_apply": "iiiipipppppppipi" "p",
     "caae_col_stats": "iipip" "p",

@@ -598,12 +598,24 @@ static inline bool vec4_ok(int C, const void* p0, int ld0, const void* p1, int l
 // One fp64 partial row per cloud.  MODE: 0 stats, 1 apply, 2 backward reduce, 3 backward apply.
 constexpr int ES_CH = 64;
 
+// Optional fused batch-norm finalize (MODE 1: forward statistics -> scale / shift; MODE 3: backward statistics -> coef):
+// every CTA reduces the fp64 partial rows of ITS 64 channels itself (fixed order), so the separate finalize launch —
+// 4 us on the step's dependent chain, eight times per step — disappears; the CTA of cloud 0 writes the per-channel
+// results (and the moving averages) for everyone else.
+struct EdgeFinalize {
+  const double* parts; int nparts; double count;
+  const float* gamma; const float* beta; float* ema_mean; float* ema_var; const float* decay;   // MODE 1
+  float* scale_out; float* shift_out; float* mean_out; float* invstd_out;                       // MODE 1
+  const float* invstd_in; float* coef_out; float* dgamma; float* dbeta;                         // MODE 3
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(1024)
 edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq, const int* __restrict__ idx,
                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef, const float* __restrict__ dOut,
-                  int lddo, float* __restrict__ out, int ldo, double* __restrict__ parts, float* __restrict__ out_lo) {
+                  int lddo, float* __restrict__ out, int ldo, double* __restrict__ parts, float* __restrict__ out_lo,
+                  const EdgeFinalize fz) {
   pdl_wait();
   extern __shared__ __align__(16) float es_smem[];
   float* Qs = es_smem;                                   // [n][ES_CH]
@@ -625,6 +637,50 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
 
   const float invk = 1.f / (float)k;
   static_assert(ES_CH == 64, "a lane owns the channel pair (2 tx, 2 tx + 1) of the 64-channel slice");
+  __shared__ float s_fz[3][ES_CH];
+  const bool fused = (MODE == 1 || MODE == 3) && fz.parts != nullptr;
+  if ((MODE == 1 || MODE == 3) && fused) {
+    // thread = (channel c of the slice, row lane r of 16): partial rows r, r + 16, ... in ascending order, then the 16 lanes
+    const int c = tid & (ES_CH - 1), r = tid >> 6;
+    double a = 0.0, b = 0.0;
+    for (int pr = r; pr < fz.nparts; pr += 16) {
+      a += fz.parts[(size_t)pr * 2 * cout + c0 + c];
+      b += fz.parts[(size_t)pr * 2 * cout + cout + c0 + c];
+    }
+    s_a[r][c] = a; s_b[r][c] = b;
+    __syncthreads();
+    if (tid < ES_CH) {
+      double s = 0.0, ss = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { s += s_a[q][tid]; ss += s_b[q][tid]; }
+      const int chg = c0 + tid;
+      if (MODE == 1) {
+        const double m = s / fz.count;
+        double v = ss / fz.count - m * m;  // biased variance, as tf.nn.moments
+        if (v < 0.0) v = 0.0;
+        const float mf = (float)m, vf = (float)v;
+        const float isd = rsqrtf(vf + kBnEps);
+        const float scv = fz.gamma[chg] * isd, shv = fz.beta[chg] - mf * scv;
+        s_fz[0][tid] = scv; s_fz[1][tid] = shv;
+        if (cloud == 0) {
+          fz.scale_out[chg] = scv; fz.shift_out[chg] = shv; fz.mean_out[chg] = mf; fz.invstd_out[chg] = isd;
+          if (fz.ema_mean != nullptr) {
+            const float d = fz.decay ? *fz.decay : 0.9f;
+            fz.ema_mean[chg] = d * fz.ema_mean[chg] + (1.f - d) * mf;
+            fz.ema_var[chg] = d * fz.ema_var[chg] + (1.f - d) * vf;
+          }
+        }
+      } else {
+        const float c0v = (float)(s / fz.count), c1v = (float)(ss / fz.count), c2v = fz.gamma[chg] * fz.invstd_in[chg];
+        s_fz[0][tid] = c0v; s_fz[1][tid] = c1v; s_fz[2][tid] = c2v;
+        if (cloud == 0) {
+          fz.coef_out[chg] = c0v; fz.coef_out[cout + chg] = c1v; fz.coef_out[2 * cout + chg] = c2v;
+          fz.dgamma[chg] = (float)ss; fz.dbeta[chg] = (float)s;
+        }
+      }
+    }
+    __syncthreads();
+  }
   {
     // one lane = two adjacent channels: the neighbour index is loaded once per pair and the gather is one LDS.64
     const int cl = 2 * tx, ch = c0 + cl;
@@ -632,9 +688,11 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
     float mdy[2] = {0.f, 0.f}, mdz[2] = {0.f, 0.f}, gis[2] = {0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      if (MODE >= 1) { sc[c] = scale[ch + c]; sh[c] = shift[ch + c]; }
+      if (MODE == 1 && fused) { sc[c] = s_fz[0][cl + c]; sh[c] = s_fz[1][cl + c]; }
+      else if (MODE >= 1) { sc[c] = scale[ch + c]; sh[c] = shift[ch + c]; }
       if (MODE >= 2) { mu[c] = mean[ch + c]; is[c] = invstd[ch + c]; }
-      if (MODE == 3) { mdy[c] = coef[ch + c]; mdz[c] = coef[cout + ch + c]; gis[c] = coef[2 * cout + ch + c]; }
+      if (MODE == 3 && fused) { mdy[c] = s_fz[0][cl + c]; mdz[c] = s_fz[1][cl + c]; gis[c] = s_fz[2][cl + c]; }
+      else if (MODE == 3) { mdy[c] = coef[ch + c]; mdz[c] = coef[cout + ch + c]; gis[c] = coef[2 * cout + ch + c]; }
     }
     double a[2] = {0.0, 0.0}, b[2] = {0.0, 0.0};
     for (int p = ty; p < n; p += 32) {
@@ -724,7 +782,7 @@ template <int MODE>
 static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
                              const float* scale, const float* shift, const float* mean, const float* invstd,
                              const float* coef, const float* dOut, int lddo, float* out, int ldo, double* parts,
-                             cudaStream_t s, float* out_lo = nullptr) {
+                             cudaStream_t s, float* out_lo = nullptr, const EdgeFinalize* fz = nullptr) {
   const size_t smem = edge_cloud_smem(n, k, MODE);
   // the kernel also holds 33 KB of static shared memory: the opt-in is needed well below 48 KB of dynamic memory
   // (a first call with n = 128 failed with "invalid argument" until a larger cloud had raised the limit).  Raised
@@ -735,8 +793,9 @@ static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int
     if (e != cudaSuccess) return (int)e;
     smem_set = smem;
   }
+  EdgeFinalize none = {};
   caae::launch(edge_cloud_kernel<MODE>, dim3(cout / ES_CH, b), dim3(32, 32), smem, s, n, k, cout, PQ, ldpq, idx, scale, shift, mean,
-                                                                          invstd, coef, dOut, lddo, out, ldo, parts, out_lo);
+               invstd, coef, dOut, lddo, out, ldo, parts, out_lo, fz ? *fz : none);
   return CAAE_LAUNCH_STATUS();
 }
 
@@ -791,6 +850,46 @@ extern "C" int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, i
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
   caae::launch(edge_apply_kernel, grid, block, 0, as_stream(stream), n, k, cout, PQ, ldpq, idx, scale, shift, out, ldo, out_lo);
   return CAAE_LAUNCH_STATUS();
+}
+
+// caae_edge_apply with the training-mode batch-norm finalize of caae_bn_finalize folded in (cloud-resident path only:
+// caae_edge_parts(...) == b): parts / nparts / count as caae_edge_stats wrote them; scale, shift, save_mean, save_invstd
+// and the moving averages are OUTPUTS.
+extern "C" int caae_edge_apply_fused(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
+                                     const double* parts, int nparts, double count, const float* gamma, const float* beta,
+                                     float* ema_mean, float* ema_var, const float* decay, float* scale, float* shift,
+                                     float* save_mean, float* save_invstd, float* out, int ldo, float* out_lo,
+                                     caae_stream_t stream) {
+  CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout || ldo < cout || nparts <= 0 || count <= 0, CAAE_E_BADSHAPE);
+  if (b == 0) return CAAE_OK;
+  CAAE_RETURN_IF(!PQ || !idx || !parts || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd || !out, CAAE_E_NULLPTR);
+  CAAE_RETURN_IF((ema_mean == nullptr) != (ema_var == nullptr), CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(!edge_cloud_ok(n, k, cout, ldpq) || !aligned16(PQ), CAAE_E_UNSUPPORTED);
+  EdgeFinalize fz = {};
+  fz.parts = parts; fz.nparts = nparts; fz.count = count; fz.gamma = gamma; fz.beta = beta; fz.ema_mean = ema_mean;
+  fz.ema_var = ema_var; fz.decay = decay; fz.scale_out = scale; fz.shift_out = shift; fz.mean_out = save_mean; fz.invstd_out = save_invstd;
+  return launch_edge_cloud<1>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out, ldo, nullptr,
+                              as_stream(stream), out_lo, &fz);
+}
+
+// caae_edge_bwd_apply with caae_bn_bwd_finalize folded in: parts as caae_edge_bwd_reduce wrote them; coef, dgamma, dbeta
+// are OUTPUTS.
+extern "C" int caae_edge_bwd_apply_fused(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
+                                         const float* scale, const float* shift, const float* mean, const float* invstd,
+                                         const double* parts, int nparts, double count, const float* gamma, float* coef,
+                                         float* dgamma, float* dbeta, const float* dOut, int lddo, float* dPQ, int lddpq,
+                                         caae_stream_t stream) {
+  CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout || lddo < cout || lddpq < 2 * cout || nparts <= 0 || count <= 0,
+                 CAAE_E_BADSHAPE);
+  if (b == 0) return CAAE_OK;
+  CAAE_RETURN_IF(!PQ || !idx || !scale || !shift || !mean || !invstd || !parts || !gamma || !coef || !dgamma || !dbeta || !dOut || !dPQ,
+                 CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(!edge_cloud_ok(n, k, cout, ldpq) || lddpq % 4 != 0 || !aligned16(PQ) || !aligned16(dPQ), CAAE_E_UNSUPPORTED);
+  EdgeFinalize fz = {};
+  fz.parts = parts; fz.nparts = nparts; fz.count = count; fz.gamma = gamma; fz.invstd_in = invstd; fz.coef_out = coef;
+  fz.dgamma = dgamma; fz.dbeta = dbeta;
+  return launch_edge_cloud<3>(b, n, k, cout, PQ, ldpq, idx, scale, shift, mean, invstd, coef, dOut, lddo, dPQ, lddpq, nullptr,
+                              as_stream(stream), nullptr, &fz);
 }
 
 extern "C" int caae_edge_bwd_reduce(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,

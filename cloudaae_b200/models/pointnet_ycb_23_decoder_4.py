@@ -234,6 +234,7 @@ class _Engine:
         # is far too small to fill 148 SMs on its own.  CLOUDAAE_STREAMS=0 serialises everything.
         self.concurrent = os.environ.get("CLOUDAAE_STREAMS", "1") != "0" and self.dev.type == "cuda"
         self.fused_stats = os.environ.get("CLOUDAAE_FUSED_STATS", "1") != "0"
+        self.fuse_finalize = os.environ.get("CLOUDAAE_FUSE_FINALIZE", "1") != "0"
         # forward GEMMs on the tensor cores: split-precision by default (CLOUDAAE_TF32X3=0: single TF32 pass)
         self.x3 = self.precision == "tf32" and os.environ.get("CLOUDAAE_TF32X3", "1") != "0"
         hi = dict(device=self.dev, priority=-1)   # the model's streams outrank the synthesis branch of a pipelined graph
@@ -523,8 +524,12 @@ class _Engine:
                     self._split(self.v[f"{s_}/weights"], fout_, fin_, fout_, lo, fout_)
         if self.model == "dgcnn":
             feat, feat_lo, ldf, cknn = x, None, D, 3
-            # clouds padded with repeats of their visible points (identical rows stay identical in every layer)
-            self._c("caae_knn_classify", B, N, D, self._p(x), D, self._p(self.knn_flags))
+            # clouds padded with repeats of their visible points (identical rows stay identical in every layer): flagged on
+            # a side stream next to the first layer's search and used for routing from the second layer on
+            sk0 = self.s_knn
+            if sk0 is not None: self._fork(sk0)
+            with self._on(sk0):
+                self._c("caae_knn_classify", B, N, D, self._p(x), D, self._p(self.knn_flags))
             with self._on(se):   # the folded weights (and the low parts of the weights) depend on the parameters only
                 for l in range(4):
                     self._c("caae_edge_fold_weights", self.cins[l], self.couts[l], self._p(self.v[f"dgcnn{l + 1}/weights"]),
@@ -543,21 +548,35 @@ class _Engine:
                 # heavily padded clouds (flagged once per forward, below) take the all-pairs kernel next to the
                 # tensor-core kernel of the others: disjoint halves of idx[l]
                 sk = self.s_knn
-                if sk is not None: self._fork(sk)
-                with self._on(sk):
-                    self._c("caae_knn_part", 2, self._p(self.knn_flags), B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
-                self._c("caae_knn_part", 1, self._p(self.knn_flags), B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
-                if sk is not None: self._join(sk)
+                if l == 0:
+                    self._c("caae_knn", B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
+                    if sk is not None: self._join(sk)     # the flags are ready long before the second layer
+                else:
+                    if sk is not None: self._fork(sk)
+                    with self._on(sk):
+                        self._c("caae_knn_part", 2, self._p(self.knn_flags), B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
+                    self._c("caae_knn_part", 1, self._p(self.knn_flags), B, N, cknn, k, self._p(feat), ldf, self._p(self.idx[l]))
+                    if sk is not None: self._join(sk)
                 if se is not None: self._join(se)
-                if train_enc:
-                    self._c("caae_edge_stats", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
-                            self._p(self.parts))
-                self._bn_coeffs(scope, train_enc, self.lib.caae_edge_parts(B, N, k, co, 2 * co), R * k, decay)
                 out = self.hcat[:, self.offs[l]:]
                 feat_lo = self.hcat_lo[:, self.offs[l]:] if self.x3 else None   # written by the same kernel
                 bn = self.bn[scope]
-                self._c("caae_edge_apply", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
-                        self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320, self._p(feat_lo))
+                nparts = self.lib.caae_edge_parts(B, N, k, co, 2 * co)
+                if train_enc:
+                    self._c("caae_edge_stats", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
+                            self._p(self.parts))
+                if train_enc and nparts == B and self.fuse_finalize:
+                    # statistics -> coefficients inside the apply kernel (no finalize launch on the dependent chain)
+                    v = self.v
+                    self._c("caae_edge_apply_fused", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
+                            self._p(self.parts), nparts, float(R * k), self._p(v[f"{scope}/bn/gamma"]), self._p(v[f"{scope}/bn/beta"]),
+                            self._p(v[f"{scope}/bn/ema_mean"]), self._p(v[f"{scope}/bn/ema_var"]), self._p(decay),
+                            self._p(bn["scale"]), self._p(bn["shift"]), self._p(bn["mean"]), self._p(bn["invstd"]),
+                            self._p(out), 320, self._p(feat_lo))
+                else:
+                    self._bn_coeffs(scope, train_enc, nparts, R * k, decay)
+                    self._c("caae_edge_apply", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
+                            self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320, self._p(feat_lo))
                 feat, ldf, cknn = out, 320, co
             scope = "dgcnn_agg"
             bn = self.bn[scope]
@@ -657,11 +676,17 @@ class _Engine:
                 args = (B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]), self._p(bn["scale"]),
                         self._p(bn["shift"]), self._p(bn["mean"]), self._p(bn["invstd"]))
                 self._c("caae_edge_bwd_reduce", *args, self._p(d_out), 320, self._p(self.parts))
-                self._c("caae_bn_bwd_finalize", co, self._p(self.parts), self.lib.caae_edge_parts(B, N, k, co, 2 * co), float(R * k),
-                        self._p(self.v[f"{scope}/bn/gamma"]), self._p(bn["invstd"]), self._p(bn["coef"]),
-                        self._p(self.v.grad_of(f"{scope}/bn/gamma")), self._p(self.v.grad_of(f"{scope}/bn/beta")))
                 d_pq, d_wf = self.d_pq[l], self.d_wf[l]
-                self._c("caae_edge_bwd_apply", *args, self._p(bn["coef"]), self._p(d_out), 320, self._p(d_pq), 2 * co)
+                nparts = self.lib.caae_edge_parts(B, N, k, co, 2 * co)
+                if nparts == B and self.fuse_finalize:
+                    self._c("caae_edge_bwd_apply_fused", *args, self._p(self.parts), nparts, float(R * k),
+                            self._p(self.v[f"{scope}/bn/gamma"]), self._p(bn["coef"]), self._p(self.v.grad_of(f"{scope}/bn/gamma")),
+                            self._p(self.v.grad_of(f"{scope}/bn/beta")), self._p(d_out), 320, self._p(d_pq), 2 * co)
+                else:
+                    self._c("caae_bn_bwd_finalize", co, self._p(self.parts), nparts, float(R * k),
+                            self._p(self.v[f"{scope}/bn/gamma"]), self._p(bn["invstd"]), self._p(bn["coef"]),
+                            self._p(self.v.grad_of(f"{scope}/bn/gamma")), self._p(self.v.grad_of(f"{scope}/bn/beta")))
+                    self._c("caae_edge_bwd_apply", *args, self._p(bn["coef"]), self._p(d_out), 320, self._p(d_pq), 2 * co)
                 feat, ldf = (self.x0, self.D) if l == 0 else (self.hcat[:, self.offs[l - 1]:], 320)
                 # dWf = X^T dPQ, then unfold to the reference's [2C, cout] weight
                 if se is not None: self._fork(se)

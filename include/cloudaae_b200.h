@@ -157,6 +157,18 @@ int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, int ldpq, co
 /* out_lo (may be NULL): out - tf32(out) with the pitch of out, the low part caae_gemm_tf32x3 reads */
 int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const float* scale,
                     const float* shift, float* out, int ldo, float* out_lo, caae_stream_t stream);
+/* caae_edge_apply / caae_edge_bwd_apply with the batch-norm finalize (caae_bn_finalize / caae_bn_bwd_finalize) folded into
+ * the kernel: every CTA reduces the partial rows of its 64 channels itself, the finalize launch leaves the dependent chain.
+ * Cloud-resident path only (caae_edge_parts(...) == b), else CAAE_E_UNSUPPORTED.  scale, shift, save_mean, save_invstd,
+ * the moving averages (forward) and coef, dgamma, dbeta (backward) are outputs. */
+int caae_edge_apply_fused(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const double* parts,
+                          int nparts, double count, const float* gamma, const float* beta, float* ema_mean, float* ema_var,
+                          const float* decay, float* scale, float* shift, float* save_mean, float* save_invstd, float* out,
+                          int ldo, float* out_lo, caae_stream_t stream);
+int caae_edge_bwd_apply_fused(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const float* scale,
+                              const float* shift, const float* mean, const float* invstd, const double* parts, int nparts,
+                              double count, const float* gamma, float* coef, float* dgamma, float* dbeta, const float* dOut,
+                              int lddo, float* dPQ, int lddpq, caae_stream_t stream);
 int caae_edge_bwd_reduce(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
                          const float* scale, const float* shift, const float* mean, const float* invstd,
                          const float* dOut, int lddo, double* parts, caae_stream_t stream);
