@@ -231,7 +231,7 @@ knn_tc_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __
   const float thresh = fminf(T + margin, 3.0e38f);     // finite: masked / padded candidates (d~ = +inf) never pass
 
   // ---- pass 2: shortlist
-  int cnt = 0, resume = KT_ROWS;
+  int cnt = 0;
   uint16_t* my_idx = sidx + row * KT_LD;
 #pragma unroll 1
   for (int ch8 = 0; ch8 < 8; ++ch8) {
@@ -245,12 +245,11 @@ knn_tc_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float d = fmaf(-2.f, __uint_as_float(r[j4 + u]), nv[u]);
-        // (rows past n carry |x_j|^2 = +inf; T itself is +inf when fewer than k groups exist).  One predicated store,
-        // no branch: entries past the capacity land in the dump slot KT_CAP of the row.
-        const bool in = (d <= thresh) && (ch8 * 32 + j4 + u < n);
-        if (in) my_idx[min(cnt, KT_CAP)] = (uint16_t)(ch8 * 32 + j4 + u);   // (slot KT_CAP ends up holding the LAST overflow entry)
-        if (in && cnt == KT_CAP) resume = ch8 * 32 + j4 + u;                // first candidate that did not fit
-        cnt += in ? 1 : 0;
+        // Six instructions per candidate: the index is stored UNCONDITIONALLY at the list's current end and the end only
+        // advances when the candidate passes (rows past n carry |x_j|^2 = +inf and thresh is finite, so they never do);
+        // entries past the capacity land in the dump slot KT_CAP of the row.
+        my_idx[min(cnt, KT_CAP)] = (uint16_t)(ch8 * 32 + j4 + u);
+        cnt += (d <= thresh) ? 1 : 0;
       }
     }
   }
@@ -303,6 +302,22 @@ knn_tc_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __
       // k selection rounds over the m entries (not m^2 rank counting: one row with m = 46 made its warp, and with it
       // the whole CTA, 2.5x slower than the median).  Entries are in ascending index order, so (key, position) is the
       // (distance, index) order; a round takes the smallest pair above the previous one.
+      if (m <= 16) {
+        // the common case (mean 11.6, p99 16 entries): keys in registers, every pair compared once, no dependent chain
+        uint32_t kr[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) kr[e] = e < m ? my_key[e] : 0xffffffffu;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          int rank = 0;
+#pragma unroll
+          for (int f = 0; f < 16; ++f) {
+            if (f < e) rank += (kr[f] <= kr[e]) ? 1 : 0;        // equal keys: the lower position (= lower index) first
+            else if (f > e) rank += (kr[f] < kr[e]) ? 1 : 0;
+          }
+          if (e < m && rank < k) out[rank] = (int)my_idx[e];
+        }
+      } else {
       unsigned long long prev = 0ull;
       for (int r = 0; r < k; ++r) {
         unsigned long long best = ~0ull;
@@ -312,6 +327,7 @@ knn_tc_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __
         }
         if (best != ~0ull) out[r] = (int)my_idx[(int)(best & 0xffull)];
         prev = best;
+      }
       }
     } else {
       // mass ties (padded duplicate points): sort the 32 collected entries in place — stable insertion sort, so equal
@@ -333,17 +349,20 @@ knn_tc_kernel(int n, int c, int k, const float* __restrict__ x, int ldx, int* __
     // a candidate with d~_j > W - |x_i|^2 + 2 eps cannot enter the list and needs no exact evaluation
     auto unsort = [](uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); };
     float tight = overflow ? fminf(thresh, unsort(my_key[k - 1]) - sq + margin) : thresh;
+    int seen = 0;                          // candidates that passed the original screen so far: the first KT_CAP are in the list
 #pragma unroll 1
     for (int ch8 = 0; ch8 < 8; ++ch8) {
       uint32_t r[32];
       tmem_ld32(trow + (uint32_t)(ch8 * 32), r);
       tmem_wait_ld(r);
-      if (overflow && ch8 * 32 + 31 >= resume) {
+      if (overflow) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int jg = ch8 * 32 + j;
           const float d = fmaf(-2.f, __uint_as_float(r[j]), nrm[jg]);
-          if (jg >= resume && jg < n && d <= tight) {
+          const bool fresh = seen >= KT_CAP;
+          seen += (d <= thresh) ? 1 : 0;
+          if (fresh && d <= tight) {
             const uint32_t key = exact_key(jg);
             if (key < my_key[k - 1]) {
               int p = k - 1;
