@@ -129,5 +129,8 @@ def test_inference_graph_replay_equals_eager_forward():
         elif k == "recon_fps":                      # the gathered picks: compare where the pick itself agrees
             same = (out["fps_idx"] == eager["fps_idx"])
             assert torch.allclose(out[k][same].double(), t[same].double(), rtol=1e-4, atol=1e-6), k
+        elif k == "chamfer":                        # ... and the chamfer terms of the clouds whose 256 picks all agree
+            same = (out["fps_idx"] == eager["fps_idx"]).all(dim=1)
+            assert same.any() and torch.allclose(out[k][same].double(), t[same].double(), rtol=1e-4, atol=1e-7), k
         else:
             assert torch.allclose(out[k].double(), t.double(), rtol=1e-4, atol=1e-6), k
