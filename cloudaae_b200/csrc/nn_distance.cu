@@ -157,7 +157,11 @@ nn_distance_bwd_smem_kernel(int n, const float* __restrict__ xyz1, int m, const 
     float v[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = live ? -__fmul_rn(__fsub_rn(B[j * 3 + c], A[j2 * 3 + c]), g) : 0.f;
-    const unsigned peers = __match_any_sync(0xffffffffu, j2);
+    // (cheap test first: collapsed outputs put equal targets on neighbouring lanes; only then the group search)
+    // (both shuffles unconditionally: a short-circuit || would let only some lanes execute the second one — a hang)
+    const int nb1 = __shfl_xor_sync(0xffffffffu, j2, 1), nb2 = __shfl_xor_sync(0xffffffffu, j2, 2);
+    const bool neighbour_hit = (j2 == nb1) | (j2 == nb2);
+    const unsigned peers = __any_sync(0xffffffffu, neighbour_hit) ? __match_any_sync(0xffffffffu, j2) : (1u << (threadIdx.x & 31));
     if (__all_sync(0xffffffffu, peers == (1u << (threadIdx.x & 31)))) {
       if (live) {
 #pragma unroll

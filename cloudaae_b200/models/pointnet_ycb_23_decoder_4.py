@@ -407,7 +407,10 @@ class _Engine:
             self._c("caae_gemm_tf32x3", 0, 0, M, N, K, self._p(A), self._p(A_lo), lda, self._p(Bm), self._p(B_lo), ldb,
                     self._p(C), ldc, self._p(bias), 0, self._p(parts))
             return True
-        self._gemm(0, 0, M, N, K, A, lda, Bm, ldb, C, ldc, bias)
+        if self.x3:   # forward values must stay fp32-grade: without the low parts the FFMA kernel, never a single TF32 pass
+            self._c("caae_gemm_f32", 0, 0, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), 0)
+        else:
+            self._gemm(0, 0, M, N, K, A, lda, Bm, ldb, C, ldc, bias)
         return False
 
     def _bn_coeffs(self, scope, training, nparts, count, decay):
