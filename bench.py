@@ -388,7 +388,8 @@ def run_ours_train(args, rank, world, local_rank):
     mode = os.environ.get("CLOUDAAE_PIPELINE", "1")
     pipelined = mode != "0"
     capture = {"0": tr.capture_online, "1": tr.capture_online_pipelined}.get(mode, tr.capture_online_decoupled)
-    static = capture(syn, *[pool_d[0][k] for k in TRAIN_KEYS])
+    kw = {"depth": int(mode)} if mode in ("2", "3", "4") else {}
+    static = capture(syn, *[pool_d[0][k] for k in TRAIN_KEYS], **kw)
 
     def load(i, src):  # refresh the graph's static pose records
         for dst, k in zip(static, TRAIN_KEYS):
@@ -1031,7 +1032,14 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        pg_options = None
+        if os.environ.get("CLOUDAAE_NCCL_MAX_CTAS"):
+            # the step is bound by SM work: fewer NCCL CTAs leave more SMs to the backward pass
+            # the bucket allreduces run next to
+            pg_options = dist.ProcessGroupNCCL.Options()
+            pg_options.config.max_ctas = int(os.environ["CLOUDAAE_NCCL_MAX_CTAS"])
+            pg_options.config.min_ctas = min(pg_options.config.max_ctas, 1)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=pg_options)
     if args.workload in ("auto", "train"):
         result = run_ours_train(args, rank, world, local_rank)
         if rank == 0 and world == 1 and os.environ.get("CLOUDAAE_BENCH_LIGHT", "0") != "1":

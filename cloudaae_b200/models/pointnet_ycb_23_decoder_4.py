@@ -235,6 +235,7 @@ class _Engine:
         self.concurrent = os.environ.get("CLOUDAAE_STREAMS", "1") != "0" and self.dev.type == "cuda"
         self.fused_stats = os.environ.get("CLOUDAAE_FUSED_STATS", "1") != "0"
         self.fuse_finalize = os.environ.get("CLOUDAAE_FUSE_FINALIZE", "1") != "0"
+        self.wgrad_floor = 1 << int(os.environ.get("CLOUDAAE_WGRAD_FLOOR", "26"))
         # forward GEMMs on the tensor cores: split-precision by default (CLOUDAAE_TF32X3=0: single TF32 pass)
         self.x3 = self.precision == "tf32" and os.environ.get("CLOUDAAE_TF32X3", "1") != "0"
         hi = dict(device=self.dev, priority=-1)   # the model's streams outrank the synthesis branch of a pipelined graph
@@ -374,7 +375,7 @@ class _Engine:
                 self._branch_backward(bi, d)
         self._heads_pending = True
 
-    def _gemm(self, ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, acc=0):
+    def _gemm(self, ta, tb, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, acc=0, floor=1 << 28):
         """Dense contraction.  precision 'tf32': the tcgen05 tensor-core kernel (TF32 multiply, fp32
         accumulate) for the LARGE contractions — in practice the three dgcnn_agg / pn_conv5 GEMMs
         (forward, data gradient, weight gradient: >90 % of the step's FLOPs).  Everything else, and
@@ -382,15 +383,15 @@ class _Engine:
         weight-bandwidth bound, and its batch-norm backward over only `batch` rows amplifies TF32
         rounding of the pre-activations far beyond the 1e-3 parity budget."""
         fn = "caae_gemm_f32"
-        if self._tensor_core(ta, tb, M, N, K, A, lda, Bm, ldb):
+        if self._tensor_core(ta, tb, M, N, K, A, lda, Bm, ldb, floor):
             fn = "caae_gemm_tf32"
         self._c(fn, ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb, self._p(C), ldc, self._p(bias), acc)
 
-    def _tensor_core(self, ta, tb, M, N, K, A, lda, Bm, ldb):
+    def _tensor_core(self, ta, tb, M, N, K, A, lda, Bm, ldb, floor=1 << 28):
         # large contractions only (>= 2^28 MACs with >= 64 output columns): besides dgcnn_agg these are the
         # EdgeConv projections and their data / weight gradients (M or K = B*N rows)
         # (never the FC stack: none of its dimensions is the B*N row count)
-        return bool(self.precision == "tf32" and M * N * K >= (1 << 28) and N >= 64 and max(M, K) >= 8192 and
+        return bool(self.precision == "tf32" and M * N * K >= floor and N >= 64 and max(M, K) >= 8192 and
                     self.lib.caae_gemm_tf32_supported(ta, tb, M, N, K, self._p(A), lda, self._p(Bm), ldb))
 
     def _split(self, x, ldx, rows, cols, lo, ldlo):
@@ -694,7 +695,9 @@ class _Engine:
                 # dWf = X^T dPQ, then unfold to the reference's [2C, cout] weight
                 if se is not None: self._fork(se)
                 with self._on(se):
-                    self._gemm(1, 0, ci, 2 * co, R, feat, ldf, d_pq, 2 * co, d_wf, 2 * co)
+                    # the first layer's [24, 128] weight gradient is a thin contraction over all B*N rows: on the FFMA
+                    # kernel its 128-row tiles are 80 % padding (35 us, step 1.891 -> 1.869 ms on tcgen05; CLOUDAAE_WGRAD_FLOOR=28 restores the FFMA route)
+                    self._gemm(1, 0, ci, 2 * co, R, feat, ldf, d_pq, 2 * co, d_wf, 2 * co, floor=self.wgrad_floor)
                     self._c("caae_edge_unfold_wgrad", ci, co, self._p(d_wf), 2 * co,
                             self._p(self.v.grad_of(f"{scope}/weights")))
                 if l > 0:  # d(net_{l-1}) += dPQ Wf^T, accumulated into its slice of d_hcat

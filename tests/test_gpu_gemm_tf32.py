@@ -21,7 +21,7 @@ def _pad4(x):
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 96), (300, 130, 77), (4096, 1024, 320), (128, 3072, 1024),
-                                   (320, 1024, 8192), (64, 64, 4096), (1, 8, 8),
+                                   (320, 1024, 8192), (64, 64, 4096), (1, 8, 8), (24, 128, 32768),
                                    (8292, 1024, 320), (20000, 256, 64), (19000, 130, 77),
                                    # the large-tile kernel: 256 x 256 (forward-like), 256 x 160 (N = 320 data gradient),
                                    # 3 x 128 rows x 128 with split-K (weight gradient, ta = 1 / tb = 0)
