@@ -1032,14 +1032,8 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        pg_options = None
-        if os.environ.get("CLOUDAAE_NCCL_MAX_CTAS"):
-            # the step is bound by SM work: fewer NCCL CTAs leave more SMs to the backward pass
-            # the bucket allreduces run next to
-            pg_options = dist.ProcessGroupNCCL.Options()
-            pg_options.config.max_ctas = int(os.environ["CLOUDAAE_NCCL_MAX_CTAS"])
-            pg_options.config.min_ctas = min(pg_options.config.max_ctas, 1)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=pg_options)
+        from cloudaae_b200.parallel import init_nccl
+        init_nccl(local_rank)   # NCCL communicator capped at 8 CTAs: the step is bound by SM work
     if args.workload in ("auto", "train"):
         result = run_ours_train(args, rank, world, local_rank)
         if rank == 0 and world == 1 and os.environ.get("CLOUDAAE_BENCH_LIGHT", "0") != "1":

@@ -6,8 +6,10 @@ exactly what SURVEY.md §8(e) calls for:
   * every cloud is independent, so FPS / gather / nn_distance / synthesis / inference shard the
     segment list by rank with NO collective (`shard_range`);
   * training is data parallel with ONE exchange: a sum-allreduce of the flat fp32 gradient buffer,
-    issued as two buckets so the first (the FC stack and pose heads — 94 % of the bytes, finished
-    early in the backward pass) overlaps the encoder backward (`BucketedAllReduce`).
+    issued as three buckets in backward order so the first (the FC stack and pose heads — 94 % of the
+    bytes, finished early in the backward pass) overlaps the encoder backward (`BucketedAllReduce`);
+  * the step is bound by SM work, not by the exchange, so the NCCL communicator is capped at a few CTAs
+    (`init_nccl`): the 26 MB bucket has the whole encoder backward (~0.5 ms) to finish in.
 """
 from __future__ import annotations
 
@@ -15,6 +17,24 @@ import os
 
 import torch
 import torch.distributed as dist
+
+
+def init_nccl(local_rank: int, max_ctas: int | None = None) -> None:
+    """torch.distributed over NCCL for one process per GPU, with the communicator capped at `max_ctas` CTAs
+    (default 8, CLOUDAAE_NCCL_MAX_CTAS overrides, 0 = NCCL's own choice).  NCCL picks 24 NVLS channels for the
+    26 MB gradient bucket on an 8-GPU NVSwitch box, i.e. 24 SMs taken from the backward pass the allreduce runs next
+    to — and the step is bound by SM work.  Measured at 8 x B200, batch 128 per GPU
+    (tools/gpu_r2_dp_ab.sh): 2.002 ms/step uncapped, 1.963 ms with 8 CTAs (single GPU: 1.869 ms)."""
+    if max_ctas is None:
+        max_ctas = int(os.environ.get("CLOUDAAE_NCCL_MAX_CTAS", "8"))
+    options = None
+    if max_ctas > 0:
+        options = dist.ProcessGroupNCCL.Options()
+        options.config.max_ctas = max_ctas
+        options.config.min_ctas = 1
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=options)
 
 
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:

@@ -20,4 +20,4 @@ for (b, n, c, ld, spread) in ((128, 256, 64, 320, 0.3), (128, 256, 64, 320, 0.01
     idx = torch.empty(b, n, 10, dtype=torch.int32, device="cuda")
     t_tc = timeit(lambda: lib.caae_knn(b, n, c, 10, x.data_ptr(), ld, idx.data_ptr(), st))
     t_ff = timeit(lambda: lib.caae_knn_ffma(b, n, c, 10, x.data_ptr(), ld, idx.data_ptr(), st))
-    print(f"b={b} n={n} c={c} spread={spread}: caae_knn (tensor-core screen + fix-up launch) {t_tc:.1f} us, FFMA kernel {t_ff:.1f} us")
+    print(f"b={b} n={n} c={c} spread={spread}: caae_knn (tensor-core screen, routed) {t_tc:.1f} us, FFMA kernel {t_ff:.1f} us")
