@@ -522,6 +522,10 @@ def run_ours_train(args, rank, world, local_rank):
         roofline = {"kernel": closed["kernel"], "bound": closed["bound"], "achieved": closed["achieved"], "peak": closed["peak"],
                     "unit": closed["unit"], "frac": closed["frac"], "traffic": traffic, "traffic_source": traffic_src,
                     "ms_per_launch": closed["us"] / 1e3, "algorithmic_flops_per_launch": agg_flops,
+                    # what the tensor pipe executes for it: the split-precision product is three MMAs per k-step
+                    # (A B + A_lo B + A B_lo) — reported beside the algorithmic figure, not instead of it
+                    "tensor_pipe": ({"mma_flops_per_launch": 3.0 * agg_flops, "achieved": 3.0 * closed["achieved"],
+                                     "frac": 3.0 * closed["frac"], "unit": "TFLOP/s"} if "tf32x3" in closed["kernel"] else None),
                     "peak_source": f"measured in this run: {tf32['how']} -> burst {tf32['tf32_tflops']:.0f} / sustained "
                                    f"{tf32['tf32_tflops_sustained']:.0f} TFLOP/s; HBM from MEASURED_PEAKS.json ({peaks['source']})",
                     "dominant_kernel_by_time": {"kernel": dom["kernel"], "us": dom["us"], "bound": dom["bound"],
