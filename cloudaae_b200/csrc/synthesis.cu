@@ -267,6 +267,7 @@ __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch
     const bool want = self < 0 && !exhausted;
     if (__any_sync(kFull, want)) {
       fetch(want, gbase, self, seq, tag, sa, sb, p);
+      __syncwarp();   // a group's lanes read what its leader (or fetch itself) wrote to shared memory
       if (want) {
         if (self < 0) exhausted = true;
         else { L = seq.length(); ui = h.U[self]; vi = h.V[self]; wi = h.W[self]; q = -1; }
@@ -340,6 +341,7 @@ __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch
     }
     const bool fin = status >= 0;
     if (__any_sync(kFull, fin)) {
+      __syncwarp();   // the leader's writes below follow every lane's reads of the slot's state in fetch
       finish(fin, gbase, self, tag, status, sa, sb);
       if (fin) self = -1;
     }
@@ -699,7 +701,8 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
             hpr::nbhd_ranges(cell_start, c % G, c / G, hpr::nbhd_halfwidth(cell_start, c), A, B);
             const int ne = state[slot];
             const unsigned key = __float_as_uint(F4[slot].w);
-            ext[slot * SY_EXTRA + ne] = (unsigned short)(key & ((1u << hpr::kPosBits) - 1u));  // same value from all 8 lanes
+            // written by the group's leader; the __syncwarp after fetch orders it before the other lanes' reads
+            if ((lane & 7) == 0) ext[slot * SY_EXTRA + ne] = (unsigned short)(key & ((1u << hpr::kPosBits) - 1u));
             seq = hpr::RangesPlusList(A, B, ext + slot * SY_EXTRA, ne + 1);
             self = i; tag = slot;
             // resume: (SA, SB) is the optimum of everything before the new constraint, which is violated
