@@ -18,8 +18,6 @@ for tool in racecheck memcheck; do
   log=gpurun_out/sanitize_$tool.log
   : > $log
   for t in "${TESTS[@]}"; do
-    # racecheck of a whole train step is an order of magnitude slower than the kernels' own tests: memcheck only
-    if [ $tool = racecheck ] && [[ "$t" == *test_train_forward* ]]; then continue; fi
     echo "=== $tool: pytest ${t%%|*} -k '${t#*|}'" >> $log
     timeout $LIMIT compute-sanitizer --tool $tool --print-limit 5 --error-exitcode 9 python -m pytest "${t%%|*}" -k "${t#*|}" -x -q -p no:cacheprovider >> $log 2>&1
     echo "=== exit $?" >> $log
