@@ -16,6 +16,7 @@
 // then one coalesced write.  No memset, no global atomics, one launch (the reference: two memsets
 // plus two launches whose batch loop is serial inside the grid).  Clouds too large for shared
 // memory take a global-atomic path.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace caae {
@@ -239,10 +240,11 @@ extern "C" int caae_nn_distance(int b, int n, const float* xyz, int m, const flo
   const long ctas4 = (long)((n + 511) / 512 + (m + 511) / 512) * b;
   const long ctas2 = (long)((n + 255) / 256 + (m + 255) / 256) * b;
   cudaStream_t s = as_stream(stream);
-  if (ctas4 >= 2 * kNumSMs) {
+  static const int forced_q = [] { const char* e = getenv("CAAE_NND_Q"); return e ? atoi(e) : 0; }();   // A/B only
+  if (forced_q ? forced_q == 4 : ctas4 >= 2 * kNumSMs) {
     dim3 grid((big + 511) / 512, b, 2);
     caae::launch(nn_distance_fwd_kernel<4>, grid, kNndThreads, 0, s, n, xyz, m, xyz2, result, result_i, result2, result2_i);
-  } else if (ctas2 >= 2 * kNumSMs) {
+  } else if (forced_q ? forced_q == 2 : ctas2 >= 2 * kNumSMs) {
     dim3 grid((big + 255) / 256, b, 2);
     caae::launch(nn_distance_fwd_kernel<2>, grid, kNndThreads, 0, s, n, xyz, m, xyz2, result, result_i, result2, result2_i);
   } else {

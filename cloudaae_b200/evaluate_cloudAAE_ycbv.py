@@ -109,6 +109,12 @@ class SegmentFrontEnd:
         idx, n_in = _radius_outliers(flt, n_flt, nb_points, radius, 512)
         inl = _gather_rows(flt, idx)
         n_flt_h, n_in_h = n_flt.tolist(), n_in.tolist()
+        # the counts are the true ones, the padded arrays hold at most `cap` points in raster order: a larger segment would
+        # silently lose its bottom rows and diverge from the reference — refuse instead (size `cap` from the label counts)
+        n_max = max(max(n_flt_h, default=0), int(e["n_org"].max()) if e["n_org"] is not None and len(n_flt_h) else 0)
+        if n_max > self.cap:
+            raise InvalidArgumentError(f"SegmentFrontEnd.run: a segment has {n_max} points but cap = {self.cap}; "
+                                       f"construct the front end with cap >= {n_max}")
         # the reference draws random.randint(0, n-1) per FPS_random call, inlier cloud first (evaluate…:288-289)
         first_in = [rng.randint(0, max(n - 1, 0)) for n in n_in_h]
         first_org = [rng.randint(0, max(min(n, self.cap) - 1, 0)) for n in n_flt_h]

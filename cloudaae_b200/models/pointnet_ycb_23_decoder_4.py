@@ -758,6 +758,10 @@ class _ModelFn(torch.autograd.Function):
         recon, rot, trans, emb, before = engine.forward(point_cloud.contiguous(), train_enc, train_fc, decay,
                                                         want_before)
         ctx.engine = engine
+        # the activations live in the engine's shared workspace: stamp them, so that a backward pass that comes after
+        # another forward (or a second backward) of the same shape fails loudly instead of using the wrong activations
+        engine.generation = getattr(engine, "generation", 0) + 1
+        ctx.generation = engine.generation
         ctx.mark_non_differentiable(*([before] if before is not None else []))
         outs = (recon.clone(), rot.clone(), trans.clone(), emb.clone())
         return outs + ((before,) if before is not None else (torch.empty(0, device=flat.device),))
@@ -765,6 +769,11 @@ class _ModelFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_recon, d_rot, d_trans, d_emb, _d_before):
         e = ctx.engine
+        if getattr(e, "generation", 0) != ctx.generation:
+            raise RuntimeError("get_model backward: the engine workspace of this (variables, batch, num_point) shape was "
+                               "overwritten by a later forward pass or already consumed by a backward pass; run "
+                               "forward -> backward one call at a time per shape")
+        e.generation += 1   # consumed: the backward pass normalises activations in place
         z = lambda g, ref: torch.zeros_like(ref) if g is None else g  # noqa: E731
         e.backward(z(d_recon, e.fc_y[e.branches[0][-1]]), z(d_rot, e.fc_y[e.branches[1][-1]]),
                    z(d_trans, e.fc_y[e.branches[2][-1]]), d_emb)

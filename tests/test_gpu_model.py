@@ -349,3 +349,21 @@ def test_knn_routing_of_padded_clouds_covers_the_batch_exactly():
         mine = (flags == (1 if part == 2 else 0))
         assert torch.equal(idx[mine], want[mine])
         assert (idx[~mine] == -1).all()
+
+
+@pytest.mark.gpu
+def test_backward_after_a_second_forward_of_the_same_shape_raises():
+    """The activations live in one workspace per (variables, batch, num_point): a backward pass against activations that a
+    later forward overwrote, or a second backward, must fail loudly instead of returning wrong gradients."""
+    b, n = 2, 256
+    v, _, visible, _, cls, _, _, noise = _setup("dgcnn", b, n, seed=9)
+    x64, _ = MR.prepare_input(visible.double(), cls, noise.double(), num_point=n)
+    x = x64.float().cuda()
+    v.flat.requires_grad_(True)
+    recon1, _, _, _ = M.get_model_dgcnn_mean_6d(x, True, True, 10, bn_decay=0.9, variables=v)
+    recon2, _, _, _ = M.get_model_dgcnn_mean_6d(x * 0.5, True, True, 10, bn_decay=0.9, variables=v)
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        recon1.sum().backward()
+    recon2.sum().backward(retain_graph=True)          # the latest forward is fine ...
+    with pytest.raises(RuntimeError, match="already consumed"):
+        recon2.sum().backward()                         # ... once
