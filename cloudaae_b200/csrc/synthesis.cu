@@ -249,10 +249,18 @@ __device__ __forceinline__ double div_pos(double a, double b) {
 //        to resume from: optimum (sa, sb) of the first p0 constraints) or self = -1 when the work list
 //        is exhausted.
 //   finish(fin, gbase, self, tag, status, sa, sb): warp-uniform call; groups with fin = true report.
+// Lanes per LP group (a power of two).  Eight is the measured choice on B200; HPR_GROUP=4 for the A/B.
+#ifndef HPR_GROUP
+#define HPR_GROUP 8
+#endif
+constexpr int kGW = HPR_GROUP;
+constexpr unsigned kGMask = (1u << kGW) - 1u;
+static_assert(kGW == 4 || kGW == 8 || kGW == 16, "group width");
+
 template <class Fetch, class Finish>
 __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch, Finish finish) {
   constexpr unsigned kFull = 0xffffffffu;
-  const int lane = threadIdx.x & 31, g = lane & 7, gbase = lane & ~7;
+  const int lane = threadIdx.x & 31, g = lane & (kGW - 1), gbase = lane & ~(kGW - 1);
   hpr::RangesPlusList seq;
   int self = -1, tag = 0, L = 0;
   bool exhausted = false;
@@ -288,8 +296,8 @@ __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch
     }
     const bool viol = valid && !clipping && r2 != 0.0 && (rhs - (sa * du + sb * dv) > 0.0);
     const bool hid = valid && !clipping && r2 == 0.0 && (dw > 0.0 || (dw == 0.0 && h.id[j] < h.id[self]));
-    const unsigned bv = (__ballot_sync(kFull, viol) >> gbase) & 0xFFu;
-    const unsigned bh = (__ballot_sync(kFull, hid) >> gbase) & 0xFFu;
+    const unsigned bv = (__ballot_sync(kFull, viol) >> gbase) & kGMask;
+    const unsigned bh = (__ballot_sync(kFull, hid) >> gbase) & kGMask;
     if (valid && clipping && r2 != 0.0) {
       const double den = da * du + db * dv, num = rhs - (p0a * du + p0b * dv);
       if (den > 0.0) { if (num * ld > ln * den) { ln = num; ld = den; } }
@@ -301,13 +309,13 @@ __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch
     int fv = 0;
     if (busy) {
       if (!clipping) {
-        fv = bv ? __ffs(bv) - 1 : 8;
-        const int fh = bh ? __ffs(bh) - 1 : 8;
+        fv = bv ? __ffs(bv) - 1 : kGW;
+        const int fh = bh ? __ffs(bh) - 1 : kGW;
         if (fh < fv) status = hpr::kLpHidden;          // a "hidden" verdict earlier than any violation
-        else if (fv == 8) { p += 8; if (p >= L) status = hpr::kLpVisible; }
+        else if (fv == kGW) { p += kGW; if (p >= L) status = hpr::kLpVisible; }
         else start_clip = true;
       } else {
-        q += 8;
+        q += kGW;
         end_clip = q >= qend;
       }
     }
@@ -328,8 +336,8 @@ __device__ __forceinline__ void hpr_solve_groups(const hpr::View& h, Fetch fetch
       const double lds = ld > 0.0 ? ld : 1.0, hds = hd > 0.0 ? hd : 1.0;
       double lo = ld > 0.0 ? div_pos(ln, lds) : -INFINITY, hi = hd > 0.0 ? div_pos(hn, hds) : INFINITY;
 #pragma unroll
-      for (int m = 1; m < 8; m <<= 1) { lo = fmax(lo, shfl_xor_d(lo, m)); hi = fmin(hi, shfl_xor_d(hi, m)); }
-      const unsigned binf = (__ballot_sync(kFull, infeas) >> gbase) & 0xFFu;
+      for (int m = 1; m < kGW; m <<= 1) { lo = fmax(lo, shfl_xor_d(lo, m)); hi = fmin(hi, shfl_xor_d(hi, m)); }
+      const unsigned binf = (__ballot_sync(kFull, infeas) >> gbase) & kGMask;
       if (end_clip) {
         if (binf || lo > hi) status = hpr::kLpHidden;
         else {
@@ -551,7 +559,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
   {
     auto fetch = [&](bool want, int gbase, int& self, hpr::RangesPlusList& seq, int& tag, double& sa, double& sb, int& p0) {
       int t = 0;
-      if (want && (lane & 7) == 0) t = atomicAdd(&s_queue, 1);
+      if (want && (lane & (kGW - 1)) == 0) t = atomicAdd(&s_queue, 1);
       t = __shfl_sync(0xffffffffu, t, gbase);
       if (want) {
         sa = 0.0; sb = 0.0; p0 = 0;
@@ -568,7 +576,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
     auto finish = [&](bool fin, int gbase, int self, int tag, int status, double sa, double sb) {
       const bool alive = fin && status == hpr::kLpVisible;
       int slot = 0;
-      if (alive && (lane & 7) == 0) {
+      if (alive && (lane & (kGW - 1)) == 0) {
         slot = atomicAdd(&s_count, 1);
         surv[slot] = (unsigned short)self; SA[slot] = sa; SB[slot] = sb; state[slot] = 0;
       }
@@ -690,7 +698,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
     {
       auto fetch = [&](bool want, int gbase, int& self, hpr::RangesPlusList& seq, int& tag, double& sa, double& sb, int& p0) {
         int t = 0;
-        if (want && (lane & 7) == 0) t = atomicAdd(&s_queue, 1);
+        if (want && (lane & (kGW - 1)) == 0) t = atomicAdd(&s_queue, 1);
         t = __shfl_sync(0xffffffffu, t, gbase);
         if (want) {
           if (t < nwork) {
@@ -702,7 +710,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
             const int ne = state[slot];
             const unsigned key = __float_as_uint(F4[slot].w);
             // written by the group's leader; the __syncwarp after fetch orders it before the other lanes' reads
-            if ((lane & 7) == 0) ext[slot * SY_EXTRA + ne] = (unsigned short)(key & ((1u << hpr::kPosBits) - 1u));
+            if ((lane & (kGW - 1)) == 0) ext[slot * SY_EXTRA + ne] = (unsigned short)(key & ((1u << hpr::kPosBits) - 1u));
             seq = hpr::RangesPlusList(A, B, ext + slot * SY_EXTRA, ne + 1);
             self = i; tag = slot;
             // resume: (SA, SB) is the optimum of everything before the new constraint, which is violated
@@ -711,7 +719,7 @@ hpr_select_kernel(const __grid_constant__ HprJobs jobs) {
         }
       };
       auto finish = [&](bool fin, int gbase, int self, int tag, int status, double sa, double sb) {
-        if (fin && (lane & 7) == 0) {
+        if (fin && (lane & (kGW - 1)) == 0) {
           F4[tag].w = 0.f;
           if (status != hpr::kLpVisible) state[tag] = kHidden;
           else {
