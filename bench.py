@@ -420,6 +420,17 @@ def run_ours_train(args, rank, world, local_rank):
         total_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
     losses = tr.losses.cpu().tolist()
+    # run-to-run spread: four more untouched repetitions of the same K steps (this rank's device time; the reported
+    # `value` is the first, contract-timed one)
+    repeats = [total_ms / args.steps]
+    for _ in range(4):
+        s.record()
+        for i in range(args.steps):
+            load(i, pool_d); tr.replay()
+        tr.join()
+        e.record()
+        torch.cuda.synchronize()
+        repeats.append(s.elapsed_time(e) / args.steps)
 
     # ---- e2e: HOST pose records (pinned) -> H2D -> synthesis + step -> D2H of the loss vector, every step
     pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in bt.items()} for bt in pool_h]
@@ -551,6 +562,8 @@ def run_ours_train(args, rank, world, local_rank):
         "roofline": roofline, "synthesis_kernel": synthesis_kernel,
         "stage_ms": dict(stage_ms, train_step_pipelined=ms),
         "losses_last_step": losses,
+        "repeat_ms_per_step": [round(x, 5) for x in repeats],   # [0] = the contract-timed run; spread of 5 x K steps
+        "spread": {"min_ms": min(repeats), "max_ms": max(repeats), "rel": (max(repeats) - min(repeats)) / min(repeats)},
         "e2e": {"value": B * world / (e2e_s / args.steps), "unit": "segments/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 16},
         "gpu_launches": int(tr.launches_per_step) * args.steps, "clocks": clocks,

@@ -280,8 +280,12 @@ extern "C" int caae_icp_refine(int b, int ns, int src_stride, const float* sourc
   CAAE_RETURN_IF((ns > 0 && source == nullptr) || (nt > 0 && target == nullptr), CAAE_E_NULLPTR);
   const size_t smem = ((size_t)ns + (size_t)nt) * 3 * sizeof(double) + (size_t)nt * sizeof(float4) + 16;
   CAAE_RETURN_IF(smem > 200 * 1024, CAAE_E_UNSUPPORTED);
-  cudaError_t e = cudaFuncSetAttribute(icp_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  static size_t smem_set = 0;   // opt in once per size class (one process per GPU), not on every call
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(icp_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
+  }
   icp_refine_kernel<<<b, kIcpThreads, smem, as_stream(stream)>>>(
       ns, src_stride, source, source_of_seg, nt, target, T_init, radius, radius_decay, outer, max_iter, rel_fitness,
       rel_rmse, T_out, fitness, inlier_rmse, iterations);

@@ -271,10 +271,12 @@ extern "C" int caae_nn_distance_grad(int b, int n, const float* xyz1, int m, con
   const int big = n > m ? n : m;
   const size_t smem = sizeof(float) * 3 * (size_t)big;
   if (smem <= 200 * 1024) {
-    if (smem > 48 * 1024) {
+    static size_t smem_set = 0;   // opt in once per size class, not on every call
+    if (smem > 48 * 1024 && smem > smem_set) {
       cudaError_t e = cudaFuncSetAttribute(nn_distance_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem);
       if (e != cudaSuccess) return (int)e;
+      smem_set = smem;
     }
     caae::launch(nn_distance_bwd_smem_kernel, dim3(2, b), kNndBwdThreads, smem, s, n, xyz1, m, xyz2, grad_dist1, idx1,
                                                                         grad_dist2, idx2, grad_xyz1, grad_xyz2);

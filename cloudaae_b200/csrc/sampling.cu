@@ -284,9 +284,11 @@ prob_sample_kernel(int n, int m, const float* __restrict__ inp_p, const float* _
 template <int PPT>
 static int launch_fps_reg(int b, int n, int m, const float* inp, int* out, float* out_xyz, cudaStream_t s) {
   const size_t smem = sizeof(float) * 3 * (size_t)n;
-  if (smem > 48 * 1024) {
+  static size_t smem_set = 0;   // per instantiation: opt in once per size class, not on every call
+  if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(fps_reg_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
   }
   caae::launch(fps_reg_kernel<PPT>, b, kFpsThreads, smem, s, n, m, inp, out, out_xyz);
   return CAAE_LAUNCH_STATUS();

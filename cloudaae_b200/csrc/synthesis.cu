@@ -851,9 +851,11 @@ static int hpr_launch(int b, int njobs, const HprJob* jobs, caae_stream_t stream
   }
   size_t smem = (size_t)nmax * SY_BYTES_PER_POINT + 8 + sizeof(int) * (2 * hpr::G * hpr::G + 1) + 16;
   smem = (smem + 15) & ~(size_t)15;
-  if (smem > 48 * 1024) {
+  static size_t smem_set = 0;   // opt in once per size class, not on every call
+  if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(hpr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
   }
   // cluster size = CTAs per cloud (CAAE_HPR_CLUSTER = 1, 2 or 4; read once).  Measured on B200, batch 128:
   // stand-alone the kernel is fastest with 2 (1.37 ms vs 1.48 ms), but next to the train step of the
