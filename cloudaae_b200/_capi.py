@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcloudaae_b200.so")
 
-ABI_VERSION = 3   # 3: split-precision forward GEMMs (caae_gemm_tf32x3, caae_split_tf32, caae_edge_apply out_lo)
+ABI_VERSION = 4   # 3: split-precision forward GEMMs (caae_gemm_tf32x3, caae_split_tf32, caae_edge_apply out_lo); 4: caae_edge_apply* record (pos_cnt, pos_sum), caae_edge_bwd_stats
 
 _int = ctypes.c_int
 _ptr = ctypes.c_void_p
@@ -53,8 +53,9 @@ _SIGNATURES = {
     "caae_debug_knn_shortlist": "iiiipipp" "p",
     "caae_knn_part": "ipiiiipip" "p",
     "caae_edge_stats": "iiiipipp" "p",
-    "caae_edge_apply": "iiiipippppip" "p",
-    "caae_edge_apply_fused": "iiiipippid" "pppppppppp" "ip" "p",
+    "caae_edge_apply": "iiiipippppip" "ppi" "p",
+    "caae_edge_apply_fused": "iiiipippid" "pppppppppp" "ip" "ppi" "p",
+    "caae_edge_bwd_stats": "iiiiipippippp" "p",
     "caae_edge_bwd_apply_fused": "iiiipip" "ppppp" "id" "pppp" "pipi" "p",
     "caae_edge_bwd_reduce": "iiiipippppppip" "p",
     "caae_edge_bwd_apply": "iiiipipppppppipi" "p",

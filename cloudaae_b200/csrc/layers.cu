@@ -609,13 +609,18 @@ struct EdgeFinalize {
   const float* invstd_in; float* coef_out; float* dgamma; float* dbeta;                         // MODE 3
 };
 
-template <int MODE>
+// REC (MODE 1 only): also record, per (point, channel), the number of neighbours with a positive activation and the sum
+// of their pre-activations z.  The layer is followed by a mean over the k neighbours, so dL/dy_ij = d_out_i / k on the
+// positive edges and the two batch-norm backward sums are  sum_i d_out_i/k * cnt_i  and  sum_i d_out_i/k * (sz_i - cnt_i mu) invstd:
+// the backward statistics become a streaming pass over [B*N, C] arrays (edge_bwd_stats_kernel) instead of a second
+// staged gather over the k-neighbour tensor (MODE 2).
+template <int MODE, bool REC = false>
 __global__ void __launch_bounds__(1024)
 edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq, const int* __restrict__ idx,
                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef, const float* __restrict__ dOut,
                   int lddo, float* __restrict__ out, int ldo, double* __restrict__ parts, float* __restrict__ out_lo,
-                  const EdgeFinalize fz) {
+                  const EdgeFinalize fz, unsigned char* __restrict__ pos_cnt, float* __restrict__ pos_sum, int ldpos) {
   pdl_wait();
   extern __shared__ __align__(16) float es_smem[];
   float* Qs = es_smem;                                   // [n][ES_CH]
@@ -717,7 +722,9 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
           if (MODE == 0) {
             fa[c] += z; fb[c] = fmaf(z, z, fb[c]);
           } else if (MODE == 1) {
-            acc[c] += fmaxf(fmaf(z, sc[c], sh[c]), 0.f);
+            const float y = fmaf(z, sc[c], sh[c]);
+            if (REC) { if (y > 0.f) { fa[c] += 1.f; fb[c] += z; } }   // the activation sum follows from (cnt, sum z) below
+            else acc[c] += fmaxf(y, 0.f);
           } else if (MODE == 2) {
             if (fmaf(z, sc[c], sh[c]) > 0.f) { fa[c] += 1.f; fb[c] += (z - mu[c]) * is[c]; }
           } else {
@@ -733,6 +740,11 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
         if (MODE == 0) { a[c] += (double)fa[c]; b[c] += (double)fb[c]; }
         if (MODE == 2) { a[c] += (double)(g[c] * fa[c]); b[c] += (double)(g[c] * fb[c]); }
       }
+      if (MODE == 1 && REC) {
+        // sum over the positive edges of (sc z + sh) = sc * sum z + sh * cnt: one accumulator less per neighbour
+#pragma unroll
+        for (int c = 0; c < 2; ++c) acc[c] = fmaxf(fmaf(sc[c], fb[c], sh[c] * fa[c]), 0.f);   // (a sum of positive terms)
+      }
       if (MODE == 1) {
         float* op = out + (base + p) * ldo + ch;
         const float v0 = acc[0] * invk, v1 = acc[1] * invk;
@@ -741,6 +753,11 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
           float* lp = out_lo + (base + p) * ldo + ch;
           lp[0] = v0 - tf32_rne(v0); lp[1] = v1 - tf32_rne(v1);
         }
+      }
+      if (MODE == 1 && REC) {
+        // (even pitch and aligned bases are checked by the entry points: one 2-byte and one 8-byte store per lane)
+        *reinterpret_cast<uchar2*>(pos_cnt + (base + p) * ldpos + ch) = make_uchar2((unsigned char)fa[0], (unsigned char)fa[1]);
+        *reinterpret_cast<float2*>(pos_sum + (base + p) * ldpos + ch) = make_float2(fb[0], fb[1]);
       }
       if (MODE == 3) *reinterpret_cast<float2*>(out + (base + p) * ldo + ch) = make_float2(acc[0], acc[1]);  // dP
     }
@@ -778,25 +795,66 @@ static inline bool edge_cloud_ok(int n, int k, int cout, int ldpq) {
 }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int MODE>
+template <int MODE, bool REC = false>
 static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
                              const float* scale, const float* shift, const float* mean, const float* invstd,
                              const float* coef, const float* dOut, int lddo, float* out, int ldo, double* parts,
-                             cudaStream_t s, float* out_lo = nullptr, const EdgeFinalize* fz = nullptr) {
+                             cudaStream_t s, float* out_lo = nullptr, const EdgeFinalize* fz = nullptr,
+                             unsigned char* pos_cnt = nullptr, float* pos_sum = nullptr, int ldpos = 0) {
   const size_t smem = edge_cloud_smem(n, k, MODE);
   // the kernel also holds 33 KB of static shared memory: the opt-in is needed well below 48 KB of dynamic memory
   // (a first call with n = 128 failed with "invalid argument" until a larger cloud had raised the limit).  Raised
   // once per size class, not per call.
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(edge_cloud_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(edge_cloud_kernel<MODE, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     smem_set = smem;
   }
   EdgeFinalize none = {};
-  caae::launch(edge_cloud_kernel<MODE>, dim3(cout / ES_CH, b), dim3(32, 32), smem, s, n, k, cout, PQ, ldpq, idx, scale, shift, mean,
-               invstd, coef, dOut, lddo, out, ldo, parts, out_lo, fz ? *fz : none);
+  caae::launch(edge_cloud_kernel<MODE, REC>, dim3(cout / ES_CH, b), dim3(32, 32), smem, s, n, k, cout, PQ, ldpq, idx, scale, shift, mean,
+               invstd, coef, dOut, lddo, out, ldo, parts, out_lo, fz ? *fz : none, pos_cnt, pos_sum, ldpos);
   return CAAE_LAUNCH_STATUS();
+}
+
+// Backward batch-norm statistics of an EdgeConv layer from what the forward apply pass recorded (see REC above): one
+// CTA per (64-channel slice, cloud), a lane owns two adjacent channels, fp64 across points, one partial row per cloud
+// in the layout of edge_cloud_kernel<2> (so caae_edge_bwd_apply[_fused] / caae_bn_bwd_finalize read it unchanged).
+__global__ void __launch_bounds__(1024)
+edge_bwd_stats_kernel(int n, int k, int cout, const float* __restrict__ dOut, int lddo,
+                      const unsigned char* __restrict__ pos_cnt, const float* __restrict__ pos_sum, int ldpos,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ parts) {
+  pdl_wait();
+  __shared__ double s_a[32][ES_CH + 1], s_b[32][ES_CH + 1];
+  const int cloud = blockIdx.y, c0 = blockIdx.x * ES_CH;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  const size_t base = (size_t)cloud * n;
+  const int cl = 2 * tx, ch = c0 + cl;
+  const float invk = 1.f / (float)k;
+  const float mu[2] = {mean[ch], mean[ch + 1]}, is[2] = {invstd[ch], invstd[ch + 1]};
+  double a[2] = {0.0, 0.0}, b[2] = {0.0, 0.0};
+  for (int p = ty; p < n; p += 32) {
+    const float* gp = dOut + (base + p) * lddo + ch;   // (a slice of a wider buffer: no alignment assumed)
+    const uchar2 c2 = *reinterpret_cast<const uchar2*>(pos_cnt + (base + p) * ldpos + ch);
+    const float2 s2 = *reinterpret_cast<const float2*>(pos_sum + (base + p) * ldpos + ch);
+    const float cv[2] = {(float)c2.x, (float)c2.y}, sv[2] = {s2.x, s2.y};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float g = gp[c] * invk, cnt = cv[c];
+      const float yhat = (sv[c] - cnt * mu[c]) * is[c];   // sum of the normalised pre-activations of the positive edges
+      a[c] += (double)(g * cnt); b[c] += (double)(g * yhat);
+    }
+  }
+  s_a[ty][cl] = a[0]; s_b[ty][cl] = b[0];
+  s_a[ty][cl + 1] = a[1]; s_b[ty][cl + 1] = b[1];
+  __syncthreads();
+  if (tid < ES_CH) {
+    double sa = 0.0, sb = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) { sa += s_a[r][tid]; sb += s_b[r][tid]; }
+    parts[(size_t)cloud * 2 * cout + c0 + tid] = sa;
+    parts[(size_t)cloud * 2 * cout + cout + c0 + tid] = sb;
+  }
 }
 
 static inline int flat_blocks(long total) {
@@ -814,6 +872,11 @@ using namespace caae;
 // cloud on the cloud-resident path, one per 32-point chunk otherwise.
 extern "C" int caae_edge_parts(int b, int n, int k, int cout, int ldpq) {
   return edge_cloud_ok(n, k, cout, ldpq) ? b : b * ((n + EDGE_PTS - 1) / EDGE_PTS);
+}
+
+// the recorded (count, sum) pairs are accessed as uchar2 / float2: even pitch, 2- / 8-byte aligned bases
+static inline bool pos_pair_ok(const void* pos_cnt, const void* pos_sum, int ldpos) {
+  return (ldpos % 2 == 0) && (reinterpret_cast<uintptr_t>(pos_cnt) & 1) == 0 && (reinterpret_cast<uintptr_t>(pos_sum) & 7) == 0;
 }
 
 static int edge_args_ok(int b, int n, int k, int cout) {
@@ -838,15 +901,22 @@ extern "C" int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, i
 
 extern "C" int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
                                const float* scale, const float* shift, float* out, int ldo, float* out_lo,
-                               caae_stream_t stream) {
+                               unsigned char* pos_cnt, float* pos_sum, int ldpos, caae_stream_t stream) {
   CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout || ldo < cout, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!PQ || !idx || !scale || !shift || !out, CAAE_E_NULLPTR);
+  CAAE_RETURN_IF((pos_cnt == nullptr) != (pos_sum == nullptr), CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(pos_cnt != nullptr && (ldpos < cout || k > 255), CAAE_E_BADSHAPE);
+  CAAE_RETURN_IF(pos_cnt != nullptr && !pos_pair_ok(pos_cnt, pos_sum, ldpos), CAAE_E_UNSUPPORTED);
   if (edge_cloud_ok(n, k, cout, ldpq)) {
     CAAE_RETURN_IF(!aligned16(PQ), CAAE_E_UNSUPPORTED);
+    if (pos_cnt != nullptr)
+      return launch_edge_cloud<1, true>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out,
+                                        ldo, nullptr, as_stream(stream), out_lo, nullptr, pos_cnt, pos_sum, ldpos);
     return launch_edge_cloud<1>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out,
                                 ldo, nullptr, as_stream(stream), out_lo);
   }
+  CAAE_RETURN_IF(pos_cnt != nullptr, CAAE_E_UNSUPPORTED);   // recording exists on the cloud-resident path only
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
   caae::launch(edge_apply_kernel, grid, block, 0, as_stream(stream), n, k, cout, PQ, ldpq, idx, scale, shift, out, ldo, out_lo);
   return CAAE_LAUNCH_STATUS();
@@ -859,7 +929,7 @@ extern "C" int caae_edge_apply_fused(int b, int n, int k, int cout, const float*
                                      const double* parts, int nparts, double count, const float* gamma, const float* beta,
                                      float* ema_mean, float* ema_var, const float* decay, float* scale, float* shift,
                                      float* save_mean, float* save_invstd, float* out, int ldo, float* out_lo,
-                                     caae_stream_t stream) {
+                                     unsigned char* pos_cnt, float* pos_sum, int ldpos, caae_stream_t stream) {
   CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout || ldo < cout || nparts <= 0 || count <= 0, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!PQ || !idx || !parts || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd || !out, CAAE_E_NULLPTR);
@@ -868,8 +938,28 @@ extern "C" int caae_edge_apply_fused(int b, int n, int k, int cout, const float*
   EdgeFinalize fz = {};
   fz.parts = parts; fz.nparts = nparts; fz.count = count; fz.gamma = gamma; fz.beta = beta; fz.ema_mean = ema_mean;
   fz.ema_var = ema_var; fz.decay = decay; fz.scale_out = scale; fz.shift_out = shift; fz.mean_out = save_mean; fz.invstd_out = save_invstd;
+  CAAE_RETURN_IF((pos_cnt == nullptr) != (pos_sum == nullptr), CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(pos_cnt != nullptr && (ldpos < cout || k > 255), CAAE_E_BADSHAPE);
+  CAAE_RETURN_IF(pos_cnt != nullptr && !pos_pair_ok(pos_cnt, pos_sum, ldpos), CAAE_E_UNSUPPORTED);
+  if (pos_cnt != nullptr)
+    return launch_edge_cloud<1, true>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out, ldo,
+                                      nullptr, as_stream(stream), out_lo, &fz, pos_cnt, pos_sum, ldpos);
   return launch_edge_cloud<1>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out, ldo, nullptr,
                               as_stream(stream), out_lo, &fz);
+}
+
+// The backward statistics of caae_edge_bwd_reduce from the (pos_cnt, pos_sum) a recording caae_edge_apply[_fused] wrote:
+// no neighbour gather, no staging.  Cloud-resident shapes only (caae_edge_parts(...) == b partial rows).
+extern "C" int caae_edge_bwd_stats(int b, int n, int k, int cout, int ldpq, const float* dOut, int lddo,
+                                   const unsigned char* pos_cnt, const float* pos_sum, int ldpos, const float* mean,
+                                   const float* invstd, double* parts, caae_stream_t stream) {
+  CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || lddo < cout || ldpos < cout, CAAE_E_BADSHAPE);
+  if (b == 0) return CAAE_OK;
+  CAAE_RETURN_IF(!dOut || !pos_cnt || !pos_sum || !mean || !invstd || !parts, CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(!edge_cloud_ok(n, k, cout, ldpq) || !pos_pair_ok(pos_cnt, pos_sum, ldpos), CAAE_E_UNSUPPORTED);
+  caae::launch(edge_bwd_stats_kernel, dim3(cout / ES_CH, b), dim3(32, 32), 0, as_stream(stream), n, k, cout, dOut, lddo, pos_cnt,
+               pos_sum, ldpos, mean, invstd, parts);
+  return CAAE_LAUNCH_STATUS();
 }
 
 // caae_edge_bwd_apply with caae_bn_bwd_finalize folded in: parts as caae_edge_bwd_reduce wrote them; coef, dgamma, dbeta

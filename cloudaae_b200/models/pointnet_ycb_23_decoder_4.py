@@ -185,6 +185,9 @@ class _Engine:
             self.yagg = torch.empty(R, 1024, **f32)
             self.pos_cnt = torch.empty(B, 1024, **f32)   # ReLU-mask statistics of the pooled layer (forward -> BN backward)
             self.pos_sum = torch.empty(B, 1024, **f32)
+            # EdgeConv layers: per (point, channel) positive-neighbour count and sum of their pre-activations (hcat's pitch)
+            self.pos_cnt_e = torch.empty(R, 320, dtype=torch.uint8, device=self.dev)
+            self.pos_sum_e = torch.empty(R, 320, **f32)
         else:
             self.enc = ["pn_conv1_encoder", "pn_conv2_encoder", "pn_conv3_encoder", "pn_conv4_encoder",
                         "pn_conv5_encoder"]
@@ -236,6 +239,11 @@ class _Engine:
         self.fused_stats = os.environ.get("CLOUDAAE_FUSED_STATS", "1") != "0"
         self.fuse_finalize = os.environ.get("CLOUDAAE_FUSE_FINALIZE", "1") != "0"
         self.wgrad_floor = 1 << int(os.environ.get("CLOUDAAE_WGRAD_FLOOR", "26"))
+        # EdgeConv: the forward apply pass records (positive-neighbour count, sum of their pre-activations) per (point,
+        # channel); the batch-norm backward sums then are a streaming pass instead of a second staged gather over the
+        # k-neighbour tensor (caae_edge_bwd_stats vs caae_edge_bwd_reduce; CLOUDAAE_EDGE_REC=0 restores the latter)
+        self.edge_rec = os.environ.get("CLOUDAAE_EDGE_REC", "1") != "0"
+        self.edge_recorded = [False] * 4
         # forward GEMMs on the tensor cores: split-precision by default (CLOUDAAE_TF32X3=0: single TF32 pass)
         self.x3 = self.precision == "tf32" and os.environ.get("CLOUDAAE_TF32X3", "1") != "0"
         hi = dict(device=self.dev, priority=-1)   # the model's streams outrank the synthesis branch of a pipelined graph
@@ -566,6 +574,10 @@ class _Engine:
                 feat_lo = self.hcat_lo[:, self.offs[l]:] if self.x3 else None   # written by the same kernel
                 bn = self.bn[scope]
                 nparts = self.lib.caae_edge_parts(B, N, k, co, 2 * co)
+                rec = train_enc and self.edge_rec and nparts == B and k <= 255
+                self.edge_recorded[l] = rec
+                rec_args = (self._p(self.pos_cnt_e[:, self.offs[l]:]), self._p(self.pos_sum_e[:, self.offs[l]:]), 320) if rec \
+                    else (None, None, 0)
                 if train_enc:
                     self._c("caae_edge_stats", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
                             self._p(self.parts))
@@ -576,11 +588,11 @@ class _Engine:
                             self._p(self.parts), nparts, float(R * k), self._p(v[f"{scope}/bn/gamma"]), self._p(v[f"{scope}/bn/beta"]),
                             self._p(v[f"{scope}/bn/ema_mean"]), self._p(v[f"{scope}/bn/ema_var"]), self._p(decay),
                             self._p(bn["scale"]), self._p(bn["shift"]), self._p(bn["mean"]), self._p(bn["invstd"]),
-                            self._p(out), 320, self._p(feat_lo))
+                            self._p(out), 320, self._p(feat_lo), *rec_args)
                 else:
                     self._bn_coeffs(scope, train_enc, nparts, R * k, decay)
                     self._c("caae_edge_apply", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
-                            self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320, self._p(feat_lo))
+                            self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320, self._p(feat_lo), *rec_args)
                 feat, ldf, cknn = out, 320, co
             scope = "dgcnn_agg"
             bn = self.bn[scope]
@@ -679,7 +691,12 @@ class _Engine:
                 d_out = self.d_hcat[:, self.offs[l]:]
                 args = (B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]), self._p(bn["scale"]),
                         self._p(bn["shift"]), self._p(bn["mean"]), self._p(bn["invstd"]))
-                self._c("caae_edge_bwd_reduce", *args, self._p(d_out), 320, self._p(self.parts))
+                if self.edge_recorded[l]:
+                    self._c("caae_edge_bwd_stats", B, N, k, co, 2 * co, self._p(d_out), 320,
+                            self._p(self.pos_cnt_e[:, self.offs[l]:]), self._p(self.pos_sum_e[:, self.offs[l]:]), 320,
+                            self._p(bn["mean"]), self._p(bn["invstd"]), self._p(self.parts))
+                else:
+                    self._c("caae_edge_bwd_reduce", *args, self._p(d_out), 320, self._p(self.parts))
                 d_pq, d_wf = self.d_pq[l], self.d_wf[l]
                 nparts = self.lib.caae_edge_parts(B, N, k, co, 2 * co)
                 if nparts == B and self.fuse_finalize:

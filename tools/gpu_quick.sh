@@ -1,9 +1,7 @@
 #!/bin/bash
-# short, hang-proof check: every command under its own small timeout
+# short, hang-proof check of the EdgeConv recording path: every command under its own small timeout
 set -u
 mkdir -p gpurun_out
-timeout 100 python -m pytest tests/test_gpu_ops.py -x -q 2>&1 | tail -2
-timeout 100 python -m pytest tests/test_gpu_model_b128.py -x -q 2>&1 | tail -2
-timeout 60 python tools/ab_pipeline.py 1 2>&1 | tail -1
-timeout 100 python bench.py --workload ops --steps 50 2>/dev/null | python -c "
-import json,sys; o=json.loads(sys.stdin.readline()); print('ops', o['value'], {k:(round(v['ms']*1e3,1), round(v.get('reference_kernel_ms',0)*1e3,1)) for k,v in o['kernels'].items()})"
+timeout 200 python -m pytest tests/test_gpu_model.py tests/test_gpu_model_b128.py tests/test_gpu_eval.py -x -q 2>&1 | tail -2
+for r in 0 1 0 1; do echo "EDGE_REC=$r $(CLOUDAAE_EDGE_REC=$r timeout 60 python tools/ab_pipeline.py 1 2>&1 | tail -1 | cut -c1-60)"; done
+timeout 200 python tools/stage_times.py --detail 2>&1 | grep -E "^L4|^L2|encoder|whole" 
