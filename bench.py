@@ -503,9 +503,9 @@ def run_ours_train(args, rank, world, local_rank):
             entry("knn xyz layer", "fp32-alu", 2.0 * B * TRAIN_N * TRAIN_N * 3, "TFLOP/s", FP32_FMA_PEAK_TFLOPS, key="L1 knn (xyz, tensor-core part)"),
             entry("EdgeConv projection GEMM 64->256 (tf32x3)", "tensor", 2.0 * R * 256 * 64, "TFLOP/s", tf32["tf32_tflops"], key="L4 proj gemm"),
             entry("edge_stats 128 ch", "hbm", R * (256 + k) * 4.0, "GB/s", hbm, key="L4 edge_stats"),
-            entry("edge_apply 128 ch", "hbm", R * ((256 + k + 2 * 128) * 4.0 + 128 * 5.0), "GB/s", hbm, key="L4 edge_apply"),
-            entry("edge_bwd_stats 128 ch (streaming pass over what the forward apply recorded)", "hbm", R * 128 * 9.0, "GB/s", hbm,
-                  key="L4 edge_bwd_stats"),
+            entry("edge_apply 128 ch", "hbm", R * (256 + k + 2 * 128) * 4.0, "GB/s", hbm, key="L4 edge_apply"),
+            entry("edge_bwd_reduce 128 ch", "hbm", R * (256 + k + 128) * 4.0, "GB/s", hbm,
+                  key="L4 edge_bwd_reduce (replaced by edge_bwd_stats)" if os.environ.get("CLOUDAAE_EDGE_REC", "0") == "1" else "L4 edge_bwd_reduce"),
             entry("edge_bwd_apply 128 ch", "hbm", R * (256 + k + 128 + 256) * 4.0, "GB/s", hbm, key="L4 edge_bwd_apply"),
             entry("dgcnn_agg forward GEMM 32768x1024x320 (tf32x3, fused BN statistics)", "tensor", agg_flops, "TFLOP/s", tf32["tf32_tflops"],
                   "algorithmic FLOPs; the split-precision product issues 3x that on the tensor pipe (parity: DESIGN 4.2)",

@@ -53,9 +53,9 @@ _SIGNATURES = {
     "caae_debug_knn_shortlist": "iiiipipp" "p",
     "caae_knn_part": "ipiiiipip" "p",
     "caae_edge_stats": "iiiipipp" "p",
-    "caae_edge_apply": "iiiipippppip" "ppi" "p",
+    "caae_edge_apply": "iiiipippppip" "p",
     "caae_edge_apply_fused": "iiiipippid" "pppppppppp" "ip" "ppi" "p",
-    "caae_edge_bwd_stats": "iiiiipippippp" "p",
+    "caae_edge_bwd_stats": "iiiiipippipp" "p",
     "caae_edge_bwd_apply_fused": "iiiipip" "ppppp" "id" "pppp" "pipi" "p",
     "caae_edge_bwd_reduce": "iiiipippppppip" "p",
     "caae_edge_bwd_apply": "iiiipipppppppipi" "p",

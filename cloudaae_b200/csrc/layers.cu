@@ -609,9 +609,9 @@ struct EdgeFinalize {
   const float* invstd_in; float* coef_out; float* dgamma; float* dbeta;                         // MODE 3
 };
 
-// REC (MODE 1 only): also record, per (point, channel), the number of neighbours with a positive activation and the sum
-// of their pre-activations z.  The layer is followed by a mean over the k neighbours, so dL/dy_ij = d_out_i / k on the
-// positive edges and the two batch-norm backward sums are  sum_i d_out_i/k * cnt_i  and  sum_i d_out_i/k * (sz_i - cnt_i mu) invstd:
+// REC (MODE 1 with the fused finalize only): also record, per (point, channel), the number of neighbours with a positive
+// activation and the sum of their pre-activations z, centred on the batch mean mu the same kernel has just finalized.  The layer is followed by a mean over the k neighbours, so dL/dy_ij = d_out_i / k on the
+// positive edges and the two batch-norm backward sums are  sum_i d_out_i/k * cnt_i  and  sum_i d_out_i/k * sz_i * invstd:
 // the backward statistics become a streaming pass over [B*N, C] arrays (edge_bwd_stats_kernel) instead of a second
 // staged gather over the k-neighbour tensor (MODE 2).
 template <int MODE, bool REC = false>
@@ -642,7 +642,7 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
 
   const float invk = 1.f / (float)k;
   static_assert(ES_CH == 64, "a lane owns the channel pair (2 tx, 2 tx + 1) of the 64-channel slice");
-  __shared__ float s_fz[3][ES_CH];
+  __shared__ float s_fz[4][ES_CH];
   const bool fused = (MODE == 1 || MODE == 3) && fz.parts != nullptr;
   if ((MODE == 1 || MODE == 3) && fused) {
     // thread = (channel c of the slice, row lane r of 16): partial rows r, r + 16, ... in ascending order, then the 16 lanes
@@ -666,7 +666,7 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
         const float mf = (float)m, vf = (float)v;
         const float isd = rsqrtf(vf + kBnEps);
         const float scv = fz.gamma[chg] * isd, shv = fz.beta[chg] - mf * scv;
-        s_fz[0][tid] = scv; s_fz[1][tid] = shv;
+        s_fz[0][tid] = scv; s_fz[1][tid] = shv; s_fz[3][tid] = mf;
         if (cloud == 0) {
           fz.scale_out[chg] = scv; fz.shift_out[chg] = shv; fz.mean_out[chg] = mf; fz.invstd_out[chg] = isd;
           if (fz.ema_mean != nullptr) {
@@ -693,7 +693,7 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
     float mdy[2] = {0.f, 0.f}, mdz[2] = {0.f, 0.f}, gis[2] = {0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      if (MODE == 1 && fused) { sc[c] = s_fz[0][cl + c]; sh[c] = s_fz[1][cl + c]; }
+      if (MODE == 1 && fused) { sc[c] = s_fz[0][cl + c]; sh[c] = s_fz[1][cl + c]; if (REC) mu[c] = s_fz[3][cl + c]; }
       else if (MODE >= 1) { sc[c] = scale[ch + c]; sh[c] = shift[ch + c]; }
       if (MODE >= 2) { mu[c] = mean[ch + c]; is[c] = invstd[ch + c]; }
       if (MODE == 3 && fused) { mdy[c] = s_fz[0][cl + c]; mdz[c] = s_fz[1][cl + c]; gis[c] = s_fz[2][cl + c]; }
@@ -723,7 +723,7 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
             fa[c] += z; fb[c] = fmaf(z, z, fb[c]);
           } else if (MODE == 1) {
             const float y = fmaf(z, sc[c], sh[c]);
-            if (REC) { if (y > 0.f) { fa[c] += 1.f; fb[c] += z; } }   // the activation sum follows from (cnt, sum z) below
+            if (REC) { if (y > 0.f) { fa[c] += 1.f; fb[c] += z - mu[c]; } }   // centred on the batch mean: no cancellation later
             else acc[c] += fmaxf(y, 0.f);
           } else if (MODE == 2) {
             if (fmaf(z, sc[c], sh[c]) > 0.f) { fa[c] += 1.f; fb[c] += (z - mu[c]) * is[c]; }
@@ -741,9 +741,9 @@ edge_cloud_kernel(int n, int k, int cout, const float* __restrict__ PQ, int ldpq
         if (MODE == 2) { a[c] += (double)(g[c] * fa[c]); b[c] += (double)(g[c] * fb[c]); }
       }
       if (MODE == 1 && REC) {
-        // sum over the positive edges of (sc z + sh) = sc * sum z + sh * cnt: one accumulator less per neighbour
+        // sum over the positive edges of (sc z + sh) = sc * sum (z - mu) + cnt * (sc mu + sh): one accumulator less per neighbour
 #pragma unroll
-        for (int c = 0; c < 2; ++c) acc[c] = fmaxf(fmaf(sc[c], fb[c], sh[c] * fa[c]), 0.f);   // (a sum of positive terms)
+        for (int c = 0; c < 2; ++c) acc[c] = fmaxf(fmaf(sc[c], fb[c], fa[c] * fmaf(sc[c], mu[c], sh[c])), 0.f);   // (a sum of positive terms)
       }
       if (MODE == 1) {
         float* op = out + (base + p) * ldo + ch;
@@ -823,7 +823,7 @@ static int launch_edge_cloud(int b, int n, int k, int cout, const float* PQ, int
 __global__ void __launch_bounds__(1024)
 edge_bwd_stats_kernel(int n, int k, int cout, const float* __restrict__ dOut, int lddo,
                       const unsigned char* __restrict__ pos_cnt, const float* __restrict__ pos_sum, int ldpos,
-                      const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ parts) {
+                      const float* __restrict__ invstd, double* __restrict__ parts) {
   pdl_wait();
   __shared__ double s_a[32][ES_CH + 1], s_b[32][ES_CH + 1];
   const int cloud = blockIdx.y, c0 = blockIdx.x * ES_CH;
@@ -831,7 +831,7 @@ edge_bwd_stats_kernel(int n, int k, int cout, const float* __restrict__ dOut, in
   const size_t base = (size_t)cloud * n;
   const int cl = 2 * tx, ch = c0 + cl;
   const float invk = 1.f / (float)k;
-  const float mu[2] = {mean[ch], mean[ch + 1]}, is[2] = {invstd[ch], invstd[ch + 1]};
+  const float is[2] = {invstd[ch], invstd[ch + 1]};
   double a[2] = {0.0, 0.0}, b[2] = {0.0, 0.0};
   for (int p = ty; p < n; p += 32) {
     const float* gp = dOut + (base + p) * lddo + ch;   // (a slice of a wider buffer: no alignment assumed)
@@ -841,7 +841,7 @@ edge_bwd_stats_kernel(int n, int k, int cout, const float* __restrict__ dOut, in
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const float g = gp[c] * invk, cnt = cv[c];
-      const float yhat = (sv[c] - cnt * mu[c]) * is[c];   // sum of the normalised pre-activations of the positive edges
+      const float yhat = sv[c] * is[c];   // sum of the normalised pre-activations of the positive edges
       a[c] += (double)(g * cnt); b[c] += (double)(g * yhat);
     }
   }
@@ -901,22 +901,15 @@ extern "C" int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, i
 
 extern "C" int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx,
                                const float* scale, const float* shift, float* out, int ldo, float* out_lo,
-                               unsigned char* pos_cnt, float* pos_sum, int ldpos, caae_stream_t stream) {
+                               caae_stream_t stream) {
   CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || ldpq < 2 * cout || ldo < cout, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
   CAAE_RETURN_IF(!PQ || !idx || !scale || !shift || !out, CAAE_E_NULLPTR);
-  CAAE_RETURN_IF((pos_cnt == nullptr) != (pos_sum == nullptr), CAAE_E_NULLPTR);
-  CAAE_RETURN_IF(pos_cnt != nullptr && (ldpos < cout || k > 255), CAAE_E_BADSHAPE);
-  CAAE_RETURN_IF(pos_cnt != nullptr && !pos_pair_ok(pos_cnt, pos_sum, ldpos), CAAE_E_UNSUPPORTED);
   if (edge_cloud_ok(n, k, cout, ldpq)) {
     CAAE_RETURN_IF(!aligned16(PQ), CAAE_E_UNSUPPORTED);
-    if (pos_cnt != nullptr)
-      return launch_edge_cloud<1, true>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out,
-                                        ldo, nullptr, as_stream(stream), out_lo, nullptr, pos_cnt, pos_sum, ldpos);
     return launch_edge_cloud<1>(b, n, k, cout, PQ, ldpq, idx, scale, shift, nullptr, nullptr, nullptr, nullptr, 0, out,
                                 ldo, nullptr, as_stream(stream), out_lo);
   }
-  CAAE_RETURN_IF(pos_cnt != nullptr, CAAE_E_UNSUPPORTED);   // recording exists on the cloud-resident path only
   dim3 grid((n + EDGE_PTS - 1) / EDGE_PTS, b), block(32, 8);
   caae::launch(edge_apply_kernel, grid, block, 0, as_stream(stream), n, k, cout, PQ, ldpq, idx, scale, shift, out, ldo, out_lo);
   return CAAE_LAUNCH_STATUS();
@@ -948,17 +941,17 @@ extern "C" int caae_edge_apply_fused(int b, int n, int k, int cout, const float*
                               as_stream(stream), out_lo, &fz);
 }
 
-// The backward statistics of caae_edge_bwd_reduce from the (pos_cnt, pos_sum) a recording caae_edge_apply[_fused] wrote:
+// The backward statistics of caae_edge_bwd_reduce from the (pos_cnt, pos_sum) a recording caae_edge_apply_fused wrote:
 // no neighbour gather, no staging.  Cloud-resident shapes only (caae_edge_parts(...) == b partial rows).
 extern "C" int caae_edge_bwd_stats(int b, int n, int k, int cout, int ldpq, const float* dOut, int lddo,
-                                   const unsigned char* pos_cnt, const float* pos_sum, int ldpos, const float* mean,
+                                   const unsigned char* pos_cnt, const float* pos_sum, int ldpos,
                                    const float* invstd, double* parts, caae_stream_t stream) {
   CAAE_RETURN_IF(!edge_args_ok(b, n, k, cout) || lddo < cout || ldpos < cout, CAAE_E_BADSHAPE);
   if (b == 0) return CAAE_OK;
-  CAAE_RETURN_IF(!dOut || !pos_cnt || !pos_sum || !mean || !invstd || !parts, CAAE_E_NULLPTR);
+  CAAE_RETURN_IF(!dOut || !pos_cnt || !pos_sum || !invstd || !parts, CAAE_E_NULLPTR);
   CAAE_RETURN_IF(!edge_cloud_ok(n, k, cout, ldpq) || !pos_pair_ok(pos_cnt, pos_sum, ldpos), CAAE_E_UNSUPPORTED);
   caae::launch(edge_bwd_stats_kernel, dim3(cout / ES_CH, b), dim3(32, 32), 0, as_stream(stream), n, k, cout, dOut, lddo, pos_cnt,
-               pos_sum, ldpos, mean, invstd, parts);
+               pos_sum, ldpos, invstd, parts);
   return CAAE_LAUNCH_STATUS();
 }
 

@@ -239,10 +239,12 @@ class _Engine:
         self.fused_stats = os.environ.get("CLOUDAAE_FUSED_STATS", "1") != "0"
         self.fuse_finalize = os.environ.get("CLOUDAAE_FUSE_FINALIZE", "1") != "0"
         self.wgrad_floor = 1 << int(os.environ.get("CLOUDAAE_WGRAD_FLOOR", "26"))
-        # EdgeConv: the forward apply pass records (positive-neighbour count, sum of their pre-activations) per (point,
-        # channel); the batch-norm backward sums then are a streaming pass instead of a second staged gather over the
-        # k-neighbour tensor (caae_edge_bwd_stats vs caae_edge_bwd_reduce; CLOUDAAE_EDGE_REC=0 restores the latter)
-        self.edge_rec = os.environ.get("CLOUDAAE_EDGE_REC", "1") != "0"
+        # EdgeConv (CLOUDAAE_EDGE_REC=1): the forward apply pass records (positive-neighbour count, centred sum of their
+        # pre-activations) per (point, channel); the batch-norm backward sums then are a streaming pass instead of a second
+        # staged gather over the k-neighbour tensor (caae_edge_bwd_stats vs caae_edge_bwd_reduce).  Measured on B200: the
+        # backward pass gets 8 / 16 us per layer shorter, the recording apply pass 2 / 9 us longer, the pipelined step is
+        # unchanged within noise (1.859 vs 1.860 ms) — so the two-gather form stays the default.
+        self.edge_rec = os.environ.get("CLOUDAAE_EDGE_REC", "0") == "1"
         self.edge_recorded = [False] * 4
         # forward GEMMs on the tensor cores: split-precision by default (CLOUDAAE_TF32X3=0: single TF32 pass)
         self.x3 = self.precision == "tf32" and os.environ.get("CLOUDAAE_TF32X3", "1") != "0"
@@ -574,7 +576,7 @@ class _Engine:
                 feat_lo = self.hcat_lo[:, self.offs[l]:] if self.x3 else None   # written by the same kernel
                 bn = self.bn[scope]
                 nparts = self.lib.caae_edge_parts(B, N, k, co, 2 * co)
-                rec = train_enc and self.edge_rec and nparts == B and k <= 255
+                rec = train_enc and self.edge_rec and nparts == B and self.fuse_finalize and k <= 255   # (the fused entry records)
                 self.edge_recorded[l] = rec
                 rec_args = (self._p(self.pos_cnt_e[:, self.offs[l]:]), self._p(self.pos_sum_e[:, self.offs[l]:]), 320) if rec \
                     else (None, None, 0)
@@ -592,7 +594,7 @@ class _Engine:
                 else:
                     self._bn_coeffs(scope, train_enc, nparts, R * k, decay)
                     self._c("caae_edge_apply", B, N, k, co, self._p(self.pq[l]), 2 * co, self._p(self.idx[l]),
-                            self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320, self._p(feat_lo), *rec_args)
+                            self._p(bn["scale"]), self._p(bn["shift"]), self._p(out), 320, self._p(feat_lo))
                 feat, ldf, cknn = out, 320, co
             scope = "dgcnn_agg"
             bn = self.bn[scope]
@@ -694,7 +696,7 @@ class _Engine:
                 if self.edge_recorded[l]:
                     self._c("caae_edge_bwd_stats", B, N, k, co, 2 * co, self._p(d_out), 320,
                             self._p(self.pos_cnt_e[:, self.offs[l]:]), self._p(self.pos_sum_e[:, self.offs[l]:]), 320,
-                            self._p(bn["mean"]), self._p(bn["invstd"]), self._p(self.parts))
+                            self._p(bn["invstd"]), self._p(self.parts))
                 else:
                     self._c("caae_edge_bwd_reduce", *args, self._p(d_out), 320, self._p(self.parts))
                 d_pq, d_wf = self.d_pq[l], self.d_wf[l]

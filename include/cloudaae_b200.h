@@ -154,17 +154,16 @@ int caae_edge_fold_weights(int c, int cout, const float* w, const float* bias, f
 int caae_edge_unfold_wgrad(int c, int cout, const float* dwf, int lddwf, float* dw, caae_stream_t stream);
 int caae_edge_stats(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, double* parts,
                     caae_stream_t stream);
-/* out_lo (may be NULL): out - tf32(out) with the pitch of out, the low part caae_gemm_tf32x3 reads.
- * pos_cnt / pos_sum (both or neither; pitch ldpos >= cout; cloud-resident shapes only): per (point, channel) the number of
- * neighbours whose activation is positive and the sum of their pre-activations — what caae_edge_bwd_stats turns into
- * the batch-norm backward sums without a second pass over the k-neighbour tensor. */
+/* out_lo (may be NULL): out - tf32(out) with the pitch of out, the low part caae_gemm_tf32x3 reads */
 int caae_edge_apply(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const float* scale,
-                    const float* shift, float* out, int ldo, float* out_lo, unsigned char* pos_cnt, float* pos_sum,
-                    int ldpos, caae_stream_t stream);
+                    const float* shift, float* out, int ldo, float* out_lo, caae_stream_t stream);
 /* caae_edge_apply / caae_edge_bwd_apply with the batch-norm finalize (caae_bn_finalize / caae_bn_bwd_finalize) folded into
  * the kernel: every CTA reduces the partial rows of its 64 channels itself, the finalize launch leaves the dependent chain.
  * Cloud-resident path only (caae_edge_parts(...) == b), else CAAE_E_UNSUPPORTED.  scale, shift, save_mean, save_invstd,
- * the moving averages (forward) and coef, dgamma, dbeta (backward) are outputs. */
+ * the moving averages (forward) and coef, dgamma, dbeta (backward) are outputs.
+ * pos_cnt / pos_sum (both or neither; even pitch ldpos >= cout): per (point, channel) the number of neighbours whose
+ * activation is positive and the sum of their pre-activations minus the batch mean — what caae_edge_bwd_stats turns into
+ * the batch-norm backward sums without a second pass over the k-neighbour tensor. */
 int caae_edge_apply_fused(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const double* parts,
                           int nparts, double count, const float* gamma, const float* beta, float* ema_mean, float* ema_var,
                           const float* decay, float* scale, float* shift, float* save_mean, float* save_invstd, float* out,
@@ -172,8 +171,7 @@ int caae_edge_apply_fused(int b, int n, int k, int cout, const float* PQ, int ld
 /* the partial rows of caae_edge_bwd_reduce (same layout, caae_edge_parts(...) == b rows) from the recorded
  * (pos_cnt, pos_sum): a streaming pass over [b*n, cout] arrays.  ldpq: the pitch of the layer's PQ (shape check only). */
 int caae_edge_bwd_stats(int b, int n, int k, int cout, int ldpq, const float* dOut, int lddo, const unsigned char* pos_cnt,
-                        const float* pos_sum, int ldpos, const float* mean, const float* invstd, double* parts,
-                        caae_stream_t stream);
+                        const float* pos_sum, int ldpos, const float* invstd, double* parts, caae_stream_t stream);
 int caae_edge_bwd_apply_fused(int b, int n, int k, int cout, const float* PQ, int ldpq, const int* idx, const float* scale,
                               const float* shift, const float* mean, const float* invstd, const double* parts, int nparts,
                               double count, const float* gamma, float* coef, float* dgamma, float* dbeta, const float* dOut,

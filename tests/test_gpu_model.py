@@ -367,3 +367,30 @@ def test_backward_after_a_second_forward_of_the_same_shape_raises():
     recon2.sum().backward(retain_graph=True)          # the latest forward is fine ...
     with pytest.raises(RuntimeError, match="already consumed"):
         recon2.sum().backward()                         # ... once
+
+
+@pytest.mark.gpu
+def test_edge_recording_path_matches_the_two_gather_path(monkeypatch):
+    """CLOUDAAE_EDGE_REC=1: the forward EdgeConv apply pass records (positive-neighbour count, centred sum of their
+    pre-activations) and the backward batch-norm sums come from a streaming pass (caae_edge_bwd_stats) instead of the
+    second gather pass (caae_edge_bwd_reduce).  Same losses, same gradients."""
+    from cloudaae_b200 import _capi
+    b, n = 4, 256
+    outs = []
+    for rec in ("0", "1"):
+        monkeypatch.setenv("CLOUDAAE_EDGE_REC", rec)
+        v, _, visible, target, cls, trans, axag, noise = _setup("dgcnn", b, n, seed=11)
+        tr = CloudAAETrainer(batch_size=b, num_point=n, model="dgcnn", variables=v, precision="fp32")
+        assert tr.engine.edge_rec == (rec == "1")
+        dev = lambda t: t.cuda().contiguous()  # noqa: E731
+        before = dict(_capi.CALLS)
+        losses = tr.forward_losses(dev(visible), dev(target), dev(cls), dev(trans), dev(axag), dev(noise)).clone()
+        tr.backward(dev(target))
+        torch.cuda.synchronize()
+        took = {k: c - before.get(k, 0) for k, c in _capi.CALLS.items()}
+        assert (took.get("caae_edge_bwd_stats", 0) == 4) == (rec == "1") and (took.get("caae_edge_bwd_reduce", 0) == 4) == (rec == "0")
+        outs.append((losses, tr.v.grad.clone(), tr.engine.hcat.clone()))
+    (l0, g0, h0), (l1, g1, h1) = outs
+    assert rel_err(h1, h0) < 1e-5                       # forward activations: sc*sum(z-mu) + cnt*(sc mu + sh) vs sum relu(sc z + sh)
+    assert torch.allclose(l0, l1, rtol=1e-5, atol=1e-7), (l0, l1)
+    assert l2_err(g1, g0) < 2e-4, l2_err(g1, g0)        # (fp32 atomics reorder sums in both runs)

@@ -170,7 +170,19 @@ def test_fused_synthesizer_feeds_training():
     assert torch.isfinite(l).all() and l[0].item() < l0[0].item() * 1.5
 
 
-def test_pipelined_graph_equals_sequential_steps():
+def _check_pipeline_losses(want, got, lr):
+    """lr = 0: the parameters never move, so every step's losses depend on that step's batch alone and must agree closely
+    (this is the sharp check of WHICH batch and WHICH Philox counters a replay used).  lr > 0: step 0 is the same
+    arithmetic; later steps drift by the summation order of the fp32 atomics (split-K reductions, EdgeConv scatter),
+    which five sign-like Adam steps at batch 8 amplify chaotically — percent-level agreement is all that can be asked."""
+    assert torch.allclose(want[0], got[0], rtol=1e-5, atol=1e-6), (want[0], got[0])
+    tol = 1e-4 if lr == 0.0 else 5e-2
+    for w, g in zip(want, got):
+        assert torch.allclose(w, g, rtol=tol, atol=1e-5), (w, g)
+
+
+@pytest.mark.parametrize("lr", [0.0, 0.0008])
+def test_pipelined_graph_equals_sequential_steps(lr):
     """capture_online_pipelined (train on batch i next to the synthesis of batch i+1, one CUDA graph) must
     produce the losses of plain sequential train_step_online calls on the same records and Philox counters."""
     from cloudaae_b200.train import CloudAAETrainer
@@ -182,12 +194,12 @@ def test_pipelined_graph_equals_sequential_steps():
         batches.append(tuple(torch.from_numpy(x).cuda() for x in (cls, ax, tr)))
 
     syn = SegmentSynthesizer(models, b, n, seed=3)
-    t_seq = CloudAAETrainer(batch_size=b, num_point=n, seed=1)
+    t_seq = CloudAAETrainer(batch_size=b, num_point=n, seed=1, learning_rate=lr)
     syn.counter.fill_(100)
     want = [t_seq.train_step_online(syn, *batches[i]).clone() for i in range(steps)]
 
     syn2 = SegmentSynthesizer(models, b, n, seed=3)
-    t_pipe = CloudAAETrainer(batch_size=b, num_point=n, seed=1)
+    t_pipe = CloudAAETrainer(batch_size=b, num_point=n, seed=1, learning_rate=lr)
     static = t_pipe.capture_online_pipelined(syn2, *batches[0])
     syn2.counter.fill_(100)
     t_pipe.prime_pipeline()                      # pending batch = batch 0, drawn with counter 101
@@ -197,15 +209,13 @@ def test_pipelined_graph_equals_sequential_steps():
             dst.copy_(src)                       # records of the NEXT batch
         got.append(t_pipe.replay().clone())
     torch.cuda.synchronize()
-    # step 0 is the same arithmetic; later steps drift by the split-K atomics' summation order, amplified by training
-    assert torch.allclose(want[0], got[0], rtol=1e-5, atol=1e-6), (want[0], got[0])
-    for w, g in zip(want, got):
-        assert torch.allclose(w, g, rtol=1e-2, atol=1e-5), (w, g)
+    _check_pipeline_losses(want, got, lr)
     assert (t_seq.v.flat - t_pipe.v.flat).abs().mean().item() < 5e-4
 
 
+@pytest.mark.parametrize("lr", [0.0, 0.0008])
 @pytest.mark.parametrize("depth", [1, 2, 3])
-def test_decoupled_two_graph_pipeline_equals_sequential_steps(depth):
+def test_decoupled_two_graph_pipeline_equals_sequential_steps(depth, lr):
     """capture_online_decoupled (synthesis and training as two graphs on two streams, `depth` batches in
     flight) must produce the losses of sequential train_step_online calls on the same records and Philox
     counters: batch k is synthesized by the k-th synthesis call in both."""
@@ -218,12 +228,12 @@ def test_decoupled_two_graph_pipeline_equals_sequential_steps(depth):
         batches.append(tuple(torch.from_numpy(x).cuda() for x in (cls, ax, tr)))
 
     syn = SegmentSynthesizer(models, b, n, seed=3)
-    t_seq = CloudAAETrainer(batch_size=b, num_point=n, seed=1)
+    t_seq = CloudAAETrainer(batch_size=b, num_point=n, seed=1, learning_rate=lr)
     syn.counter.fill_(100)
     want = [t_seq.train_step_online(syn, *batches[i]).clone() for i in range(steps)]
 
     syn2 = SegmentSynthesizer(models, b, n, seed=3)
-    t_dec = CloudAAETrainer(batch_size=b, num_point=n, seed=1)
+    t_dec = CloudAAETrainer(batch_size=b, num_point=n, seed=1, learning_rate=lr)
     static = t_dec.capture_online_decoupled(syn2, *batches[0], depth=depth)
     syn2.counter.fill_(100)
     t_dec.prime_pipeline(batches[:depth])        # queue = batches 0..depth-1, drawn with counters 101..
@@ -234,7 +244,5 @@ def test_decoupled_two_graph_pipeline_equals_sequential_steps(depth):
         got.append(t_dec.replay().clone())
     t_dec.join()
     torch.cuda.synchronize()
-    assert torch.allclose(want[0], got[0], rtol=1e-5, atol=1e-6), (want[0], got[0])
-    for w, g in zip(want, got):
-        assert torch.allclose(w, g, rtol=1e-2, atol=1e-5), (w, g)
+    _check_pipeline_losses(want, got, lr)
     assert (t_seq.v.flat - t_dec.v.flat).abs().mean().item() < 5e-4   # (fp32 atomics reorder sums; Adam's first steps are sign-like)

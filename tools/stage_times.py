@@ -116,9 +116,9 @@ def measure(tr, syn, c, ax, tl, iters=30, detail=True):
                 (f"L{l + 1} proj gemm", lambda feat=feat, l=l, ci=ci, co=co: eng._gemm_fwd(R, 2 * co, ci, feat, eng.hcat_lo[:, eng.offs[l - 1]:] if eng.x3 else None, 320, eng.wf[l], eng.wf_lo[l], 2 * co, eng.pq[l], 2 * co, eng.bf[l])),
                 (f"L{l + 1} edge_stats", lambda l=l, co=co: eng._c("caae_edge_stats", B, N, k, co, p(eng.pq[l]), 2 * co, p(eng.idx[l]), p(eng.parts))),
                 (f"L{l + 1} bn_finalize", lambda scope=scope, nparts=nparts: eng._bn_coeffs(scope, True, nparts, R * k, tr.decay)),
-                (f"L{l + 1} edge_apply", lambda l=l, co=co, bn=bn: eng._c("caae_edge_apply", B, N, k, co, p(eng.pq[l]), 2 * co, p(eng.idx[l]), p(bn["scale"]), p(bn["shift"]), p(eng.hcat[:, eng.offs[l]:]), 320, p(eng.hcat_lo[:, eng.offs[l]:]), p(eng.pos_cnt_e[:, eng.offs[l]:]), p(eng.pos_sum_e[:, eng.offs[l]:]), 320)),
-                (f"L{l + 1} edge_bwd_stats", lambda d_out=d_out, bn=bn, l=l, co=co: eng._c("caae_edge_bwd_stats", B, N, k, co, 2 * co, p(d_out), 320, p(eng.pos_cnt_e[:, eng.offs[l]:]), p(eng.pos_sum_e[:, eng.offs[l]:]), 320, p(bn["mean"]), p(bn["invstd"]), p(eng.parts))),
-                (f"L{l + 1} edge_bwd_reduce (replaced by edge_bwd_stats)", lambda args=args, d_out=d_out: eng._c("caae_edge_bwd_reduce", *args, p(d_out), 320, p(eng.parts))),
+                (f"L{l + 1} edge_apply", lambda l=l, co=co, bn=bn, scope=scope, nparts=nparts: eng._c("caae_edge_apply_fused", B, N, k, co, p(eng.pq[l]), 2 * co, p(eng.idx[l]), p(eng.parts), nparts, float(R * k), p(eng.v[f"{scope}/bn/gamma"]), p(eng.v[f"{scope}/bn/beta"]), None, None, p(tr.decay), p(bn["scale"]), p(bn["shift"]), p(bn["mean"]), p(bn["invstd"]), p(eng.hcat[:, eng.offs[l]:]), 320, p(eng.hcat_lo[:, eng.offs[l]:]), *((p(eng.pos_cnt_e[:, eng.offs[l]:]), p(eng.pos_sum_e[:, eng.offs[l]:]), 320) if eng.edge_rec else (None, None, 0)))),
+                (f"L{l + 1} edge_bwd_stats", lambda d_out=d_out, bn=bn, l=l, co=co: eng._c("caae_edge_bwd_stats", B, N, k, co, 2 * co, p(d_out), 320, p(eng.pos_cnt_e[:, eng.offs[l]:]), p(eng.pos_sum_e[:, eng.offs[l]:]), 320, p(bn["invstd"]), p(eng.parts))),
+                (f"L{l + 1} edge_bwd_reduce" + (" (replaced by edge_bwd_stats)" if eng.edge_rec else ""), lambda args=args, d_out=d_out: eng._c("caae_edge_bwd_reduce", *args, p(d_out), 320, p(eng.parts))),
                 (f"L{l + 1} edge_bwd_apply", lambda args=args, d_out=d_out, bn=bn, l=l, co=co: eng._c("caae_edge_bwd_apply", *args, p(bn["coef"]), p(d_out), 320, p(eng.d_pq[l]), 2 * co)),
                 (f"L{l + 1} wgrad gemm", lambda feat=feat, l=l, ci=ci, co=co: eng._gemm(1, 0, ci, 2 * co, R, feat, 320, eng.d_pq[l], 2 * co, eng.d_wf[l], 2 * co)),
                 (f"L{l + 1} dgrad gemm", lambda l=l, ci=ci, co=co: eng._gemm(0, 1, R, ci, 2 * co, eng.d_pq[l], 2 * co, eng.wf[l], 2 * co, eng.d_hcat[:, eng.offs[l - 1]:], 320, None, 1)),
