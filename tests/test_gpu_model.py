@@ -393,4 +393,4 @@ def test_edge_recording_path_matches_the_two_gather_path(monkeypatch):
     (l0, g0, h0), (l1, g1, h1) = outs
     assert rel_err(h1, h0) < 1e-5                       # forward activations: sc*sum(z-mu) + cnt*(sc mu + sh) vs sum relu(sc z + sh)
     assert torch.allclose(l0, l1, rtol=1e-5, atol=1e-7), (l0, l1)
-    assert l2_err(g1, g0) < 2e-4, l2_err(g1, g0)        # (fp32 atomics reorder sums in both runs)
+    assert l2_err(g1, g0) < 1e-3, l2_err(g1, g0)        # the north-star tolerance (fp32 atomics reorder sums in both runs)
