@@ -20,11 +20,17 @@ using namespace caae::hpr;
 // stats i64[b,8]: {n_unique, phase1 iterations, survivors, dirty survivors, phase3 iterations,
 //                  max re-solve rounds of one point, slow-path (fp64) evaluations in phase 2, full-LP fallbacks}
 // iters_out (optional) i32[b,n]: phase-1 loop iterations of the point at each SORTED position (-1 past n_unique).
-extern "C" int hpr_host_iters(const float* flipped, int b, int n, unsigned char* flags, long long* stats, int* iters_out);
-extern "C" int hpr_host(const float* flipped, int b, int n, unsigned char* flags, long long* stats) {
-  return hpr_host_iters(flipped, b, n, flags, stats, nullptr);
-}
+// ids_out (optional) i32[b,n]: original index of the point at each SORTED position (-1 past n_unique).
+extern "C" int hpr_host_iters_ids(const float* flipped, int b, int n, unsigned char* flags, long long* stats, int* iters_out,
+                                  int* ids_out);
 extern "C" int hpr_host_iters(const float* flipped, int b, int n, unsigned char* flags, long long* stats, int* iters_out) {
+  return hpr_host_iters_ids(flipped, b, n, flags, stats, iters_out, nullptr);
+}
+extern "C" int hpr_host(const float* flipped, int b, int n, unsigned char* flags, long long* stats) {
+  return hpr_host_iters_ids(flipped, b, n, flags, stats, nullptr, nullptr);
+}
+extern "C" int hpr_host_iters_ids(const float* flipped, int b, int n, unsigned char* flags, long long* stats, int* iters_out,
+                                  int* ids_out) {
   for (int cloud = 0; cloud < b; ++cloud) {
     const float* f = flipped + (size_t)cloud * n * 3;
     unsigned char* flag = flags + (size_t)cloud * n;
@@ -50,6 +56,12 @@ extern "C" int hpr_host_iters(const float* flipped, int b, int n, unsigned char*
       cell[i] = cy * G + cx;
       members[cell[i]].push_back(i);  // ascending index
     }
+    // (experiment, HPR_ORDER_W=1: inside a cell the points nearest to the viewer — largest lifted w — first, so that the
+    //  constraints most likely to hide a point are met early; the kernel's order is ascending index)
+    static const int order_w = std::getenv("HPR_ORDER_W") ? std::atoi(std::getenv("HPR_ORDER_W")) : 0;
+    if (order_w)
+      for (int c = 0; c < G * G; ++c)
+        std::stable_sort(members[c].begin(), members[c].end(), [&](int a, int b2) { return order_w > 0 ? w[a] > w[b2] : w[a] < w[b2]; });
     // exact duplicates: only the lowest index of identical points takes part
     std::vector<int> cell_start(G * G + 1, 0);
     std::vector<unsigned short> id;
@@ -78,6 +90,7 @@ extern "C" int hpr_host_iters(const float* flipped, int b, int n, unsigned char*
     View h{U.data(), V.data(), W.data(), id.data(), cell_start.data(), rho, nu};
     st[0] = nu;
     if (iters_out) for (int p = 0; p < n; ++p) iters_out[(size_t)cloud * n + p] = -1;
+    if (ids_out) for (int p = 0; p < n; ++p) ids_out[(size_t)cloud * n + p] = p < nu ? (int)id[p] : -1;
     const float kh = 0.5f * (float)rho;
     std::vector<float> fzrow(G, -3.4e38f);
     for (int p = 0; p < nu; ++p) fzrow[cell_of[p] / G] = std::max(fzrow[cell_of[p] / G], F[4 * p + 2]);
