@@ -147,7 +147,9 @@ int caae_debug_knn_shortlist(int b, int n, int c, int k, const float* x, int ldx
 int caae_knn_part(int part, const int* flags, int b, int n, int c, int k, const float* x, int ldx, int* idx,
                   caae_stream_t stream);
 
-/* EdgeConv on the factorised projection PQ [b*n, >=2*cout] = [P | Q]: z_ij = P_i + Q_nn(i,j). */
+/* EdgeConv = get_edge_feature + conv2d 1x1 + batch norm + ReLU + mean over the k neighbours (utils/tf_util.py:635-669,
+ * 111-179, 473-511; models/pointnet_ycb_23_decoder_4.py:337-404) on the factorised projection
+ * PQ [b*n, >=2*cout] = [P | Q]:  concat(x_i, x_j - x_i) W = x_i (W_top - W_bot) + x_j W_bot,  z_ij = P_i + Q_nn(i,j). */
 int caae_edge_parts(int b, int n, int k, int cout, int ldpq); /* fp64 partial rows caae_edge_stats / _bwd_reduce write */
 int caae_edge_fold_weights(int c, int cout, const float* w, const float* bias, float* wf, float* bias_f, int ldw,
                            caae_stream_t stream);
