@@ -19,19 +19,26 @@ import torch
 import torch.distributed as dist
 
 
+def nccl_options(max_ctas: int | None = None):
+    """ProcessGroupNCCL options with the communicator's CTA count capped (None: CLOUDAAE_NCCL_MAX_CTAS, default 8;
+    0: no cap -> returns None, NCCL chooses)."""
+    if max_ctas is None:
+        max_ctas = int(os.environ.get("CLOUDAAE_NCCL_MAX_CTAS", "8"))
+    if max_ctas <= 0:
+        return None
+    options = dist.ProcessGroupNCCL.Options()
+    options.config.max_ctas = max_ctas
+    options.config.min_ctas = 1
+    return options
+
+
 def init_nccl(local_rank: int, max_ctas: int | None = None) -> None:
     """torch.distributed over NCCL for one process per GPU, with the communicator capped at `max_ctas` CTAs
     (default 8, CLOUDAAE_NCCL_MAX_CTAS overrides, 0 = NCCL's own choice).  NCCL picks 24 NVLS channels for the
     26 MB gradient bucket on an 8-GPU NVSwitch box, i.e. 24 SMs taken from the backward pass the allreduce runs next
     to — and the step is bound by SM work.  Measured at 8 x B200, batch 128 per GPU
     (tools/gpu_r2_dp_ab.sh): 2.002 ms/step uncapped, 1.963 ms with 8 CTAs (single GPU: 1.869 ms)."""
-    if max_ctas is None:
-        max_ctas = int(os.environ.get("CLOUDAAE_NCCL_MAX_CTAS", "8"))
-    options = None
-    if max_ctas > 0:
-        options = dist.ProcessGroupNCCL.Options()
-        options.config.max_ctas = max_ctas
-        options.config.min_ctas = 1
+    options = nccl_options(max_ctas)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=options)

@@ -75,3 +75,19 @@ def test_gloo_world2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_nccl_options_cap_the_communicator_ctas(monkeypatch):
+    """The data-parallel step is bound by SM work, so the NCCL communicator is capped at a few CTAs: default 8,
+    CLOUDAAE_NCCL_MAX_CTAS overrides, 0 leaves the choice to NCCL."""
+    from cloudaae_b200 import parallel
+    if not hasattr(torch.distributed, "ProcessGroupNCCL"):
+        pytest.skip("torch built without NCCL")
+    monkeypatch.delenv("CLOUDAAE_NCCL_MAX_CTAS", raising=False)
+    o = parallel.nccl_options()
+    assert o.config.max_ctas == 8 and o.config.min_ctas == 1
+    monkeypatch.setenv("CLOUDAAE_NCCL_MAX_CTAS", "4")
+    assert parallel.nccl_options().config.max_ctas == 4
+    monkeypatch.setenv("CLOUDAAE_NCCL_MAX_CTAS", "0")
+    assert parallel.nccl_options() is None
+    assert parallel.nccl_options(16).config.max_ctas == 16
